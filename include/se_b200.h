@@ -1,0 +1,126 @@
+/* se_b200.h -- C-ABI of the B200-native spectral front/back-end (libse_b200.so).
+ *
+ * The reference (ooshyun/Speech-Enhancement-Pytorch) has NO native / FFI layer for this path:
+ * its "operator API" is four Python call signatures.  Each entry point below
+ * names the reference interface it replaces; INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (unless stated), on the device that
+ *     is current when the call is made; `stream` is a cudaStream_t passed as void*;
+ *   - calls are asynchronous on `stream`, re-entrant, and keep no global scratch (constant
+ *     tables per (device, n_fft, hop, win_length, scale) live behind a mutex-guarded cache);
+ *   - inputs are never written; outputs are fully overwritten (unless `accumulate` != 0);
+ *   - return value 0 = ok, negative = se_status; se_last_error() gives the message of the last
+ *     failing call on the calling thread.  No exceptions cross this boundary;
+ *   - `rows` = product of all leading dims (batch x [speakers x] channels), SURVEY.md 8 notation:
+ *     N = nsample, n = n_fft, h = hop, F = n/2+1, T = nframe = 1 + N/h (centre=True).
+ *   - supported: n_fft in {512,1024,2048}, hop in {n/4, n/2}, 2 <= win_length <= n_fft,
+ *     centre=True only.  Anything else returns SE_ERR_UNSUPPORTED (there is no fallback).
+ */
+#ifndef SE_B200_H
+#define SE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum se_status {
+    SE_OK = 0,
+    SE_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, inconsistent shape */
+    SE_ERR_UNSUPPORTED = -2,  /* n_fft / hop / win_length / mode outside the supported set */
+    SE_ERR_CUDA = -3,         /* launch or runtime failure; message holds cudaGetErrorString */
+    SE_ERR_ENVELOPE = -4      /* window overlap-add envelope ~ 0 (torch.istft raises the same) */
+} se_status;
+
+typedef enum se_mask_mode {   /* SURVEY.md 8a row a5 */
+    SE_MASK_REAL = 0,         /* Y = X * m           unet.py:62 dnn.py:140 stft_rnn.py:108 crn.py:139 */
+    SE_MASK_E = 1,            /* polar               dcunet.py:136-155 dccrn.py:203-217 */
+    SE_MASK_C = 2,            /* complex multiply    dcunet.py:156-157 dccrn.py:218-219 */
+    SE_MASK_R = 3             /* re*mr, im*mi        dcunet.py:158-159 dccrn.py:220-221 */
+} se_mask_mode;
+
+typedef enum se_spec_layout {
+    SE_LAYOUT_FT2 = 0,        /* [rows, F, T, 2]  torch.stft real view (src/evaluate.py:109-126) */
+    SE_LAYOUT_PLANAR = 1      /* [rows, 2F, T]    DCCRN conv layout, Re bins then Im bins (dccrn.py:691) */
+} se_spec_layout;
+
+int se_version(void);
+const char* se_last_error(void);
+
+/* ---- replaces torch.stft inside stft_custom(tensor, config), src/evaluate.py:101-128 --------
+ * x [rows,N] -> spec [rows,F,T,2] = scale * rfft(hann(win_length) * reflect-padded frames).
+ * The reference uses scale = 1/win_length (src/evaluate.py:120). */
+int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop,
+                int win_length, float scale, void* stream);
+
+/* adjoint of se_stft_fwd (autograd of src/evaluate.py:109-120):
+ * gspec [rows,F,T,2] (dL/dRe, dL/dIm) -> gx [rows,N]; accumulate != 0 adds into gx. */
+int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop,
+                int win_length, float scale, int accumulate, void* stream);
+
+/* ---- replaces torch.istft inside istft_custom(tensor, length, config), src/evaluate.py:130-162
+ * spec [rows,F,T,2] -> y [rows,length] = OLA(hann * irfft(scale * spec)) / OLA(hann^2),
+ * trimmed by n/2, zero-extended past the natural end.  Reference scale = win_length (:131). */
+int se_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t length, int n_fft,
+                 int hop, int win_length, float scale, void* stream);
+
+/* adjoint of se_istft_fwd: gy [rows,length] -> gspec [rows,F,T,2] */
+int se_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t length, int n_fft,
+                 int hop, int win_length, float scale, void* stream);
+
+/* ---- mask application (model forward tails) -----------------------------------
+ * spec/out [count,2]; mask [count] (REAL) or [count,2] (E/C/R).  pre_tanh: mask = tanh(raw)
+ * first (src/model/dcunet.py:131).  count = rows*F*T. */
+int se_mask_fwd(const float* spec, const float* mask, float* out, int64_t count, int mode, int pre_tanh,
+                void* stream);
+/* gout [count,2] -> gmask (same shape as mask, gradient wrt the RAW mask) and, if gspec != NULL,
+ * gspec [count,2]. */
+int se_mask_bwd(const float* spec, const float* mask, const float* gout, float* gmask, float* gspec,
+                int64_t count, int mode, int pre_tanh, void* stream);
+
+/* ---- multi-resolution STFT loss (new component; calling convention loss_function(enhanced,
+ * sources), src/solver.py:480; definition SURVEY.md 8c).  Resolutions are fixed:
+ * (512,128,512) (1024,256,1024) (2048,512,2048).
+ *   fwd   : est, ref [rows,N] -> sums[9] (device, double): per resolution
+ *           sum (b-a)^2, sum b^2, sum |log b - log a|.  Deterministic two-stage reduction.
+ *           workspace: se_mrstft_workspace_bytes(rows, nsample) bytes of device scratch.
+ *   value : sums (after the caller all-reduced them across ranks) -> loss (device float).
+ *           global_rows = rows summed over ranks (sets the mean's denominator).
+ *   bwd   : g_est [rows,N] = gout * dloss/dest, gout a DEVICE scalar (upstream gradient). */
+int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample);
+int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums,
+                       void* workspace, void* stream);
+int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsample, float* loss, void* stream);
+int se_mrstft_loss_bwd(const float* est, const float* ref, const double* sums, const float* gout,
+                       int64_t global_rows, int64_t rows, int64_t nsample, float* g_est, void* stream);
+
+/* ---- fused wave -> STFT -> mask -> iSTFT -> wave (stft_custom + model tail + istft_custom in
+ * one launch; SURVEY.md 8b "se_enhance_fwd/bwd").  mask [rows,F,T] (REAL) or [rows,F,T,2].
+ * The 1/win_length and win_length scales of the reference cancel and are not applied. */
+int se_enhance_fwd(const float* x, const float* mask, float* y, int64_t rows, int64_t nsample, int n_fft,
+                   int hop, int win_length, int mode, int pre_tanh, void* stream);
+/* gy [rows,N], x, mask -> gmask (gradient wrt the raw mask) */
+int se_enhance_bwd(const float* gy, const float* x, const float* mask, float* gmask, int64_t rows,
+                   int64_t nsample, int n_fft, int hop, int win_length, int mode, int pre_tanh, void* stream);
+
+/* ---- DCCRN in-model transforms: ConvSTFT.forward / ConviSTFT.forward, src/model/dccrn.py:687-747
+ * x [rows,N] -> spec [rows, 2F, T], T = (N + 2(win_len-win_inc) - win_len)/win_inc + 1, Hann
+ * window, zero padding, frame zero-extended at the END to fft_len.  Supported: fft_len 512,
+ * win_len <= fft_len, even win_inc. */
+int se_conv_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int win_len, int win_inc,
+                     int fft_len, void* stream);
+/* spec [rows,2F,T] -> y [rows,out_len]; out_len = length if length > 0 else natural
+ * (win_inc*(T-1) + win_len - 2(win_len-win_inc)).  Least-squares (pinv) frame inverse,
+ * window^2 overlap-add normalisation with the reference's +1e-8 (dccrn.py:733-745). */
+int se_conv_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t out_len,
+                      int win_len, int win_inc, int fft_len, void* stream);
+int se_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t out_len,
+                      int win_len, int win_inc, int fft_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H */

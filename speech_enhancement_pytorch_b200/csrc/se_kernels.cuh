@@ -1,0 +1,635 @@
+// se_kernels.cuh -- the spectral kernels built on the frame-interleaved FFT engine (se_fft.cuh).
+//
+// Coordinates: every transform works in PADDED coordinates i (reflect / zero padded signal, i = 0
+// is the first sample of frame 0); frame t covers i in [t*HOP, t*HOP + N); "block" b is the
+// hop-sized span [b*HOP, (b+1)*HOP).  A CTA owns one row and a contiguous chunk of it and walks
+// the chunk in groups of 16 frames.
+#pragma once
+#include "se_fft.cuh"
+
+namespace se {
+
+enum LoadMode { LOAD_REFLECT = 0, LOAD_ZEROPAD = 1, LOAD_ENV = 2 };
+enum EmitMode { EMIT_ISTFT = 0, EMIT_ADJ = 1 };
+
+struct Tables {
+    const float* win;       // window (placed in n_fft, scaled per op kind), N floats
+    const float2* tw;       // exp(-2 pi i k / M), k < M
+    const float2* twn;      // exp(-2 pi i k / N), k < M
+    const float* w2;        // unscaled window^2, N floats
+    const float* inv_env;   // 1 / sum_q w2[o + q*HOP], HOP floats
+};
+
+struct AnaArgs {            // analysis: waveform-like -> spectrum
+    Tables tb;
+    const float* in;        // [rows, in_len]
+    float* out;             // spectrum
+    int64_t in_stride;      // floats between rows of `in`
+    int nsample;            // N (REFLECT / ZEROPAD: valid input samples; ENV: natural padded length)
+    int in_len;             // ENV: `length` of gy rows
+    int nframe;             // T
+    int pad;                // ZEROPAD: zeros in front
+    int gpc, nchunks;       // groups per chunk, chunks per row
+    float edge_scale;       // multiplies DC and Nyquist outputs
+};
+
+struct SynArgs {            // synthesis: spectrum -> waveform-like
+    Tables tb;
+    const float* in;        // spectrum [rows, F, T, 2]
+    float* out;             // [rows, out_len]
+    int nsample;            // ADJ: N ; ISTFT: natural padded length n + hop (T-1)
+    int out_len;            // ISTFT: length ; ADJ: N
+    int nframe;             // T
+    int b_lo, b_hi;         // emitted block range per row
+    int nchunks;
+    int accumulate;
+    float edge_scale;       // multiplies DC / Nyquist inputs
+};
+
+// ------------------------------------------------------------------ padded-signal samplers
+__device__ __forceinline__ float sample_reflect(const float* __restrict__ x, int n_half, int N, int n_fft, int i) {
+    if (i < 0 || i >= N + n_fft) return 0.f;
+    int j = i - n_half;
+    j = j < 0 ? -j : j;
+    j = j >= N ? 2 * (N - 1) - j : j;
+    return __ldg(x + j);
+}
+
+template <class G>
+__device__ __forceinline__ float inv_env_at(const Tables& tb, int T, int i) {
+    const int b = i / G::HOP, o = i - b * G::HOP;
+    if (b >= G::OLA - 1 && b <= T - 1) return __ldg(tb.inv_env + o);
+    float e = 0.f;
+#pragma unroll
+    for (int q = 0; q < G::OLA; ++q) {
+        const int t = b - q;
+        if (t >= 0 && t < T) e += __ldg(tb.w2 + o + q * G::HOP);
+    }
+    return e > 0.f ? 1.0f / e : 0.f;
+}
+
+// Fill the hop-row-padded stage with padded coordinates [p0, p0 + SROWS*HOP).
+template <class G, int LMODE>
+__device__ __forceinline__ void fill_stage(float* __restrict__ stage, const float* __restrict__ src,
+                                           int p0, const AnaArgs& a, int tid) {
+    for (int rel = 2 * tid; rel < G::SROWS * G::HOP; rel += 2 * G::NT) {
+        const int i = p0 + rel;
+        float v0, v1;
+        if (LMODE == LOAD_REFLECT) {
+            const int j = i - G::N / 2;
+            if (j >= 0 && j + 1 < a.nsample) {
+                v0 = __ldg(src + j);
+                v1 = __ldg(src + j + 1);
+            } else {
+                v0 = sample_reflect(src, G::N / 2, a.nsample, G::N, i);
+                v1 = sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1);
+            }
+        } else if (LMODE == LOAD_ZEROPAD) {
+            const int j = i - a.pad;
+            v0 = (j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f;
+            v1 = (j + 1 >= 0 && j + 1 < a.nsample) ? __ldg(src + j + 1) : 0.f;
+        } else {   // LOAD_ENV: gy / envelope placed at n/2 inside the natural padded length
+            const int s = i - G::N / 2;
+            v0 = (s >= 0 && s < a.in_len && i < a.nsample) ? __ldg(src + s) * inv_env_at<G>(a.tb, a.nframe, i) : 0.f;
+            v1 = (s + 1 >= 0 && s + 1 < a.in_len && i + 1 < a.nsample)
+                     ? __ldg(src + s + 1) * inv_env_at<G>(a.tb, a.nframe, i + 1) : 0.f;
+        }
+        *reinterpret_cast<float2*>(stage + (rel / G::HOP) * G::SROW + rel % G::HOP) = make_float2(v0, v1);
+    }
+}
+
+// ------------------------------------------------------------------ spectrum row I/O
+// interleaved [F][T] float2
+template <class G>
+__device__ __forceinline__ void store_task_ft2(float2* __restrict__ row, int T, int t, int p,
+                                               const float2* xa, const float2* xb, float2 nyq, float edge) {
+    if (t < 0 || t >= T) return;
+    const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        float2 v = xa[k4];
+        if (p == 0 && k4 == 0) v = make_float2(v.x * edge, 0.f);
+        row[(size_t)(qa + G::S * k4) * T + t] = v;
+        row[(size_t)(qb + G::S * k4) * T + t] = xb[k4];
+    }
+    if (p == 0) row[(size_t)G::M * T + t] = make_float2(nyq.x * edge, 0.f);
+}
+// planar [2F][T] floats (DCCRN)
+template <class G>
+__device__ __forceinline__ void store_task_planar(float* __restrict__ row, int T, int t, int p,
+                                                  const float2* xa, const float2* xb, float2 nyq) {
+    if (t < 0 || t >= T) return;
+    const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        const int ka = qa + G::S * k4, kb = qb + G::S * k4;
+        row[(size_t)ka * T + t] = xa[k4].x;
+        row[(size_t)(G::F + ka) * T + t] = xa[k4].y;
+        row[(size_t)kb * T + t] = xb[k4].x;
+        row[(size_t)(G::F + kb) * T + t] = xb[k4].y;
+    }
+    if (p == 0) {
+        row[(size_t)G::M * T + t] = nyq.x;
+        row[(size_t)(G::F + G::M) * T + t] = 0.f;
+    }
+}
+template <class G>
+__device__ __forceinline__ void load_task_ft2(const float2* __restrict__ row, int T, int t, int p,
+                                              float2* ya, float2* yb, float2& nyq, float edge) {
+    const bool ok = (t >= 0 && t < T);
+    const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        ya[k4] = ok ? __ldg(row + (size_t)(qa + G::S * k4) * T + t) : make_float2(0.f, 0.f);
+        yb[k4] = ok ? __ldg(row + (size_t)(qb + G::S * k4) * T + t) : make_float2(0.f, 0.f);
+    }
+    nyq = make_float2(0.f, 0.f);
+    if (p == 0) {
+        if (ok) nyq = __ldg(row + (size_t)G::M * T + t);
+        ya[0].x *= edge;
+        nyq.x *= edge;
+    }
+}
+
+// ------------------------------------------------------------------ analysis group (stage -> registers)
+// After this call zb holds pass-B output; the caller runs pass C per paired task.
+template <class G>
+__device__ __forceinline__ void analysis_passes(const float* stage, const Tables& tb, float2* zb, int unit, int fr) {
+    passA_fwd<G>(stage, tb.win, tb.tw, zb, unit, fr);
+    __syncthreads();
+    passB_fwd<G>(tb.tw, zb, unit, fr);
+    __syncthreads();
+}
+template <class G>
+__device__ __forceinline__ void analysis_task(const float2* zb, const Tables& tb, int p, int fr,
+                                              float2* xa, float2* xb, float2& nyq) {
+    passC_fwd_unit<G>(zb, task_qa<G>(p), fr, xa);
+    passC_fwd_unit<G>(zb, task_qb<G>(p), fr, xb);
+    split_task<G>(p, tb.twn, xa, xb, nyq);
+}
+// synthesis: registers -> zb (pass C'), then B', then per-task A' + OLA into ostage
+template <class G>
+__device__ __forceinline__ void synthesis_task(float2* zb, const Tables& tb, int p, int fr,
+                                               float2* ya, float2* yb, float2 nyq) {
+    merge_task<G>(p, tb.twn, ya, yb, nyq);
+    passC_inv_unit<G>(zb, task_qa<G>(p), fr, ya);
+    passC_inv_unit<G>(zb, task_qb<G>(p), fr, yb);
+}
+template <class G>
+__device__ __forceinline__ void synthesis_tail(float2* zb, const Tables& tb, float* ostage, int unit, int fr,
+                                               float2 (*carry)[G::SEG]) {
+    __syncthreads();
+    passB_inv<G>(tb.tw, zb, unit, fr);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i) {
+        const int u = unit + i * G::NU;
+        float2 v[G::R1], acc[G::SEG];
+        passA_inv_task<G>(zb, tb.win, tb.tw, u, fr, v);
+        ola_rotate<G>(v, fr, carry[i], acc);
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s)
+            *reinterpret_cast<float2*>(ostage + fr * G::SROW + 2 * (u + 64 * s)) = acc[s];
+    }
+    __syncthreads();
+}
+
+// chunk geometry shared by all synthesis-type kernels
+struct Chunk { int b0, b1, f0, ngroups; bool first, last; };
+template <class G>
+__device__ __forceinline__ Chunk make_chunk(int chunk, int nchunks, int b_lo, int b_hi) {
+    Chunk c;
+    const int nb = b_hi - b_lo;
+    c.b0 = b_lo + (int)(((int64_t)chunk * nb) / nchunks);
+    c.b1 = b_lo + (int)(((int64_t)(chunk + 1) * nb) / nchunks);
+    c.f0 = c.b0 - (G::OLA - 1);
+    c.ngroups = (c.b1 - c.f0 + G::FR - 1) / G::FR;
+    c.first = chunk == 0;
+    c.last = chunk == nchunks - 1;
+    return c;
+}
+
+// ------------------------------------------------------------------ emitters
+template <class G>
+__device__ __forceinline__ void emit_istft(const float* __restrict__ ostage, float* __restrict__ y_row,
+                                           int f_base, const Chunk& c, const SynArgs& a, int tid) {
+    for (int idx = tid; idx < G::FR * G::HOP; idx += G::NT) {
+        const int blk = idx / G::HOP, o = idx - blk * G::HOP;
+        const int b = f_base + blk;
+        if (b < c.b0 || b >= c.b1) continue;
+        const int i = b * G::HOP + o;
+        const int s = i - G::N / 2;
+        if (s < 0 || s >= a.out_len) continue;
+        float r = 0.f;
+        if (i < a.nsample) r = ostage[blk * G::SROW + o] * inv_env_at<G>(a.tb, a.nframe, i);
+        y_row[s] = r;
+    }
+}
+
+// adjoint emitter: fold the reflect padding back.  hold[] keeps the right-edge zone until the
+// row's last group (its mirror sources arrive later than its destinations).
+template <class G>
+__device__ __forceinline__ void emit_adj(const float* __restrict__ ostage, float* __restrict__ hold,
+                                         float* __restrict__ gx_row, int f_base, const Chunk& c,
+                                         int N, int accumulate, float gain, int tid) {
+    constexpr int NH = G::N / 2;
+    const int zs = ((N - 1) / G::HOP) * G::HOP;
+    for (int idx = tid; idx < G::FR * G::HOP; idx += G::NT) {
+        const int blk = idx / G::HOP, o = idx - blk * G::HOP;
+        const int b = f_base + blk;
+        if (b < c.b0 || b >= c.b1) continue;
+        const int i = b * G::HOP + o;
+        if (i >= N + G::N) continue;
+        float v = ostage[blk * G::SROW + o];
+        if (i > NH && i <= G::N) {                       // left mirror: x[j] also fed p[n/2 - j]
+            const int is = G::N - i;                      // source padded coordinate, < n/2
+            const int sb = is / G::HOP - f_base;          // always inside this (first) group
+            v += ostage[sb * G::SROW + is % G::HOP];
+        }
+        if (c.last && i >= zs) {
+            hold[i - zs] = v;
+        } else if (i >= NH) {
+            const int j = i - NH;
+            gx_row[j] = accumulate ? gx_row[j] + v * gain : v * gain;
+        }
+    }
+}
+template <class G>
+__device__ __forceinline__ void finish_adj(const float* __restrict__ hold, float* __restrict__ gx_row, int N,
+                                           int accumulate, float gain, int tid) {
+    constexpr int NH = G::N / 2;
+    const int zs = ((N - 1) / G::HOP) * G::HOP;
+    for (int i = zs + tid; i < N + NH; i += G::NT) {
+        float v = hold[i - zs];
+        if (i >= N - 1 && i <= N + NH - 2) v += hold[(2 * N + G::N - 2 - i) - zs];   // right mirror
+        const int j = i - NH;
+        gx_row[j] = accumulate ? gx_row[j] + v * gain : v * gain;
+    }
+}
+
+// ------------------------------------------------------------------ smem carve-up
+template <class G> struct Smem {
+    static constexpr size_t ZB = sizeof(float) * G::ZB_FLOATS;
+    static constexpr size_t STAGE = sizeof(float) * G::STAGE_FLOATS;
+    static constexpr size_t OSTAGE = sizeof(float) * G::OSTAGE_FLOATS;
+    static constexpr size_t HOLD = sizeof(float) * (G::N + 2 * G::HOP);
+    static constexpr size_t ANALYSIS = ZB + STAGE;
+    static constexpr size_t SYNTH_ISTFT = ZB + OSTAGE;
+    static constexpr size_t SYNTH_ADJ = ZB + OSTAGE + HOLD;
+    // fused analysis+synthesis: stage and ostage are never live together -> aliased
+    static constexpr size_t IOBUF = STAGE > OSTAGE ? STAGE : OSTAGE;
+    static constexpr size_t FUSED_ADJ = ZB + IOBUF + HOLD;
+    static constexpr size_t FUSED_ISTFT = ZB + IOBUF;
+};
+
+// ================================================================== kernels
+// wave-like rows -> spectrum.  LMODE picks the padded-signal definition, PLANAR the layout.
+template <class G, int LMODE, bool PLANAR>
+__global__ void __launch_bounds__(G::NT) k_analysis(const AnaArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    const float* src = a.in + (size_t)row * a.in_stride;
+    for (int g = 0; g < a.gpc; ++g) {
+        const int f_base = (chunk * a.gpc + g) * G::FR;
+        if (f_base >= a.nframe) break;
+        fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid);
+        __syncthreads();
+        analysis_passes<G>(stage, a.tb, zb, unit, fr);
+        const int t = f_base + fr;
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            if (PLANAR) store_task_planar<G>(a.out + (size_t)row * 2 * G::F * a.nframe, a.nframe, t, p, xa, xb, nyq);
+            else store_task_ft2<G>(reinterpret_cast<float2*>(a.out) + (size_t)row * G::F * a.nframe, a.nframe, t, p,
+                                   xa, xb, nyq, a.edge_scale);
+        }
+        __syncthreads();
+    }
+}
+
+// spectrum -> wave-like rows.  EMODE: ISTFT (envelope + trim) or ADJ (reflect fold-back).
+template <class G, int EMODE>
+__global__ void __launch_bounds__(G::NT) k_synthesis(const SynArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::OSTAGE);
+    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
+    const float2* spec = reinterpret_cast<const float2*>(a.in) + (size_t)row * G::F * a.nframe;
+    float* out_row = a.out + (size_t)row * a.out_len;
+    float2 carry[G::TA][G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i)
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
+    for (int g = 0; g < c.ngroups; ++g) {
+        const int f_base = c.f0 + g * G::FR;
+        const int t = f_base + fr;
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 ya[8], yb[8], nyq;
+            load_task_ft2<G>(spec, a.nframe, t, p, ya, yb, nyq, a.edge_scale);
+            synthesis_task<G>(zb, a.tb, p, fr, ya, yb, nyq);
+        }
+        synthesis_tail<G>(zb, a.tb, ostage, unit, fr, carry);
+        if (EMODE == EMIT_ISTFT) emit_istft<G>(ostage, out_row, f_base, c, a, tid);
+        else emit_adj<G>(ostage, hold, out_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
+    }
+    if (EMODE == EMIT_ADJ && c.last) {
+        __syncthreads();
+        finish_adj<G>(hold, out_row, a.nsample, a.accumulate, 1.0f, tid);
+    }
+}
+
+// ------------------------------------------------------------------ MR-STFT loss
+struct LossArgs {
+    Tables tb;
+    const float* est;
+    const float* ref;
+    float* g_est;            // bwd
+    double* partials;        // fwd: [grid][3]
+    const double* sums;      // bwd: this resolution's 3 sums
+    const float* gout;       // bwd: device scalar
+    int nsample, nframe;
+    int gpc, nchunks;        // fwd chunking (analysis style)
+    int b_lo, b_hi;          // bwd chunking (synthesis style)
+    int accumulate;
+    float inv_count;         // 1 / (global_rows * F * T)
+    float inv_res;           // 1 / number of resolutions
+};
+#define SE_MRSTFT_CLAMP 1e-7f
+
+template <class G>
+__global__ void __launch_bounds__(G::NT) k_loss_fwd(const LossArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    __shared__ float red[3][32];
+    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    AnaArgs la;
+    la.tb = a.tb; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;
+    float s_d2 = 0.f, s_b2 = 0.f, s_lm = 0.f;
+    for (int g = 0; g < a.gpc; ++g) {
+        const int f_base = (chunk * a.gpc + g) * G::FR;
+        if (f_base >= a.nframe) break;
+        const int t = f_base + fr;
+        float pb[G::TC][17];
+        fill_stage<G, LOAD_REFLECT>(stage, a.ref + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+        __syncthreads();
+        analysis_passes<G>(stage, a.tb, zb, unit, fr);
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                pb[i][k4] = xa[k4].x * xa[k4].x + xa[k4].y * xa[k4].y;
+                pb[i][8 + k4] = xb[k4].x * xb[k4].x + xb[k4].y * xb[k4].y;
+            }
+            pb[i][16] = nyq.x * nyq.x;
+        }
+        fill_stage<G, LOAD_REFLECT>(stage, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+        __syncthreads();
+        analysis_passes<G>(stage, a.tb, zb, unit, fr);
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            if (t < a.nframe) {
+#pragma unroll
+                for (int k = 0; k < 17; ++k) {
+                    if (k == 16 && p != 0) continue;
+                    const float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                    const float ca = fmaxf(v.x * v.x + v.y * v.y, SE_MRSTFT_CLAMP);
+                    const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
+                    const float ma = sqrtf(ca), mb = sqrtf(cb);
+                    const float d = mb - ma;
+                    s_d2 += d * d;
+                    s_b2 += cb;
+                    s_lm += 0.5f * fabsf(logf(cb) - logf(ca));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // block reduction -> one deterministic partial per CTA
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        s_d2 += __shfl_xor_sync(0xffffffffu, s_d2, m);
+        s_b2 += __shfl_xor_sync(0xffffffffu, s_b2, m);
+        s_lm += __shfl_xor_sync(0xffffffffu, s_lm, m);
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = s_d2; red[1][tid >> 5] = s_b2; red[2][tid >> 5] = s_lm; }
+    __syncthreads();
+    if (tid < 3) {
+        double acc = 0.0;
+        for (int w = 0; w < G::NT / 32; ++w) acc += (double)red[tid][w];
+        a.partials[(size_t)blockIdx.x * 3 + tid] = acc;
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::NT) k_loss_bwd(const LossArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);          // stage, later ostage
+    float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::IOBUF);
+    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
+    AnaArgs la;
+    la.tb = a.tb; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;
+    // dL/da = gs * [ alpha (a - b) + beta sign(a - b) / a ]
+    const double d2 = a.sums[0], b2 = a.sums[1];
+    const float gs = __ldg(a.gout) * a.inv_res;
+    const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
+    const float beta = gs * a.inv_count;
+    float* gx_row = a.g_est + (size_t)row * a.nsample;
+    float2 carry[G::TA][G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i)
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
+    for (int g = 0; g < c.ngroups; ++g) {
+        const int f_base = c.f0 + g * G::FR;
+        const int t = f_base + fr;
+        const bool live = (t >= 0 && t < a.nframe);
+        float pb[G::TC][17];
+        fill_stage<G, LOAD_REFLECT>(iobuf, a.ref + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+        __syncthreads();
+        analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                pb[i][k4] = xa[k4].x * xa[k4].x + xa[k4].y * xa[k4].y;
+                pb[i][8 + k4] = xb[k4].x * xb[k4].x + xb[k4].y * xb[k4].y;
+            }
+            pb[i][16] = nyq.x * nyq.x;
+        }
+        fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+        __syncthreads();
+        analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+#pragma unroll
+            for (int k = 0; k < 17; ++k) {
+                float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                const float pa = v.x * v.x + v.y * v.y;
+                float coef = 0.f;
+                if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
+                    const float ma = sqrtf(pa), mb = sqrtf(fmaxf(pb[i][k], SE_MRSTFT_CLAMP));
+                    const float sg = ma > mb ? 1.f : (ma < mb ? -1.f : 0.f);
+                    coef = (alpha * (ma - mb) + beta * sg / ma) / ma;
+                }
+                // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
+                if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
+                v = make_float2(v.x * coef, v.y * coef);
+                if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
+            }
+            synthesis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+        }
+        synthesis_tail<G>(zb, a.tb, iobuf, unit, fr, carry);
+        emit_adj<G>(iobuf, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
+        __syncthreads();
+    }
+    if (c.last) {
+        finish_adj<G>(hold, gx_row, a.nsample, a.accumulate, 1.0f, tid);
+    }
+}
+
+// reduce per-CTA partials -> sums[3] in a fixed order (one CTA, deterministic)
+__global__ void k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict__ sums) {
+    __shared__ double sh[3][256];
+    const int tid = threadIdx.x;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int i = tid; i < n; i += 256)
+        for (int j = 0; j < 3; ++j) acc[j] += partials[(size_t)i * 3 + j];
+    for (int j = 0; j < 3; ++j) sh[j][tid] = acc[j];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (tid < s)
+            for (int j = 0; j < 3; ++j) sh[j][tid] += sh[j][tid + s];
+        __syncthreads();
+    }
+    if (tid < 3) sums[tid] = sh[tid][0];
+}
+
+__global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double cnt[3] = {c0, c1, c2};
+        double total = 0.0;
+        for (int r = 0; r < 3; ++r) {
+            const double d2 = sums[3 * r], b2 = sums[3 * r + 1], lm = sums[3 * r + 2];
+            total += sqrt(d2) / sqrt(b2) + lm / cnt[r];
+        }
+        *loss = (float)(total / 3.0);
+    }
+}
+
+// ------------------------------------------------------------------ masks (elementwise)
+struct MaskMath {
+    // y = f(x, m); m already squashed.  E: tanh(|m|) sqrt(|x|^2+1e-8) (x/|x|)(m/|m|)
+    __device__ static __forceinline__ float2 unit(float2 v, float p) {
+        if (p > 1e-30f) { const float r = 1.0f / sqrtf(p); return make_float2(v.x * r, v.y * r); }
+        const float s = fmaxf(fabsf(v.x), fabsf(v.y));
+        if (s == 0.f) return make_float2(1.f, 0.f);
+        const float ax = v.x / s, ay = v.y / s;
+        const float r = 1.0f / sqrtf(ax * ax + ay * ay);
+        return make_float2(ax * r, ay * r);
+    }
+    __device__ static __forceinline__ float2 fwd(int mode, float2 x, float2 m) {
+        if (mode == 2) return cmul(x, m);
+        if (mode == 3) return make_float2(x.x * m.x, x.y * m.y);
+        const float px = x.x * x.x + x.y * x.y, pm = m.x * m.x + m.y * m.y;
+        const float2 ux = unit(x, px), um = unit(m, pm);
+        const float gain = tanhf(sqrtf(pm)) * sqrtf(px + 1e-8f);
+        const float2 u = cmul(ux, um);
+        return make_float2(gain * u.x, gain * u.y);
+    }
+    // gradient wrt m (squashed) and optionally x, given gy
+    __device__ static __forceinline__ void bwd(int mode, float2 x, float2 m, float2 gy, float2& gm, float2& gx) {
+        if (mode == 2) { gm = cmulc(gy, x); gx = cmulc(gy, m); return; }
+        if (mode == 3) { gm = make_float2(x.x * gy.x, x.y * gy.y); gx = make_float2(m.x * gy.x, m.y * gy.y); return; }
+        const float px = x.x * x.x + x.y * x.y, pm = m.x * m.x + m.y * m.y;
+        const float2 ux = unit(x, px), um = unit(m, pm);
+        const float mag = sqrtf(px + 1e-8f), r = sqrtf(pm), th = tanhf(r);
+        // h = phi(r) m, phi = tanh(r)/r ; y = (mag ux) * h
+        float phi, dphi_r;                       // dphi_r = phi'(r) / r
+        if (r < 0.05f) { phi = 1.f - pm * (1.f / 3.f) + pm * pm * (2.f / 15.f); dphi_r = -2.f / 3.f + pm * (8.f / 15.f); }
+        else { phi = th / r; dphi_r = ((1.f - th * th) * r - th) / (r * pm); }
+        const float2 cx = make_float2(mag * ux.x, mag * ux.y);
+        const float2 gh = cmulc(gy, cx);         // conj(cx) * gy
+        const float dot = m.x * gh.x + m.y * gh.y;
+        gm = make_float2(phi * gh.x + dphi_r * dot * m.x, phi * gh.y + dphi_r * dot * m.y);
+        // k = psi(rho) x, psi = mag / rho ; y = h * k
+        const float2 h = make_float2(th * um.x, th * um.y);
+        const float2 gk = cmulc(gy, h);
+        if (px > 1e-30f) {
+            const float rho = sqrtf(px), psi = mag / rho, dpsi_r = -1e-8f / (rho * px * mag);
+            const float dx = x.x * gk.x + x.y * gk.y;
+            gx = make_float2(psi * gk.x + dpsi_r * dx * x.x, psi * gk.y + dpsi_r * dx * x.y);
+        } else gx = make_float2(0.f, 0.f);
+    }
+};
+
+__global__ void __launch_bounds__(256) k_mask_fwd(const float2* __restrict__ spec, const float* __restrict__ mask,
+                                                  float2* __restrict__ out, int64_t count, int mode, int pre_tanh) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float2 x = __ldg(spec + i);
+        if (mode == 0) {
+            float m = __ldg(mask + i);
+            if (pre_tanh) m = tanhf(m);
+            out[i] = make_float2(x.x * m, x.y * m);
+        } else {
+            float2 m = __ldg(reinterpret_cast<const float2*>(mask) + i);
+            if (pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
+            out[i] = MaskMath::fwd(mode, x, m);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mask_bwd(const float2* __restrict__ spec, const float* __restrict__ mask,
+                                                  const float2* __restrict__ gout, float* __restrict__ gmask,
+                                                  float2* __restrict__ gspec, int64_t count, int mode, int pre_tanh) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const float2 x = __ldg(spec + i), gy = __ldg(gout + i);
+        if (mode == 0) {
+            float m = __ldg(mask + i);
+            if (pre_tanh) m = tanhf(m);
+            float gm = x.x * gy.x + x.y * gy.y;
+            if (pre_tanh) gm *= (1.f - m * m);
+            gmask[i] = gm;
+            if (gspec) gspec[i] = make_float2(gy.x * m, gy.y * m);
+        } else {
+            float2 m = __ldg(reinterpret_cast<const float2*>(mask) + i);
+            if (pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
+            float2 gm, gx;
+            MaskMath::bwd(mode, x, m, gy, gm, gx);
+            if (pre_tanh) gm = make_float2(gm.x * (1.f - m.x * m.x), gm.y * (1.f - m.y * m.y));
+            reinterpret_cast<float2*>(gmask)[i] = gm;
+            if (gspec) gspec[i] = gx;
+        }
+    }
+}
+
+}  // namespace se

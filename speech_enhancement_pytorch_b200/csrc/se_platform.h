@@ -1,0 +1,39 @@
+// se_platform.h -- CUDA runtime include + launch helper.
+//
+// The product is built with nvcc for sm_100a.  With -DSE_EMULATE (tests/cuda_emu, g++ only, no
+// GPU) the same sources compile against a fiber-based emulator so kernel index math can be
+// debugged in the build container; that build is test infrastructure and never shipped/loaded
+// by the package.
+#pragma once
+
+#ifdef SE_EMULATE
+#include "cuda_emu.h"
+#define SE_SMEM_DECL unsigned char* se_smem = emu::g_dyn_smem
+#else
+#include <cuda_runtime.h>
+#define SE_SMEM_DECL extern __shared__ __align__(16) unsigned char se_smem[]
+#endif
+
+#include <cstddef>
+#include <cstdint>
+
+namespace se {
+
+template <class... Params, class... Args>
+inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block, size_t smem,
+                          cudaStream_t stream, Args... args) {
+#ifdef SE_EMULATE
+    (void)stream;
+    emu::launch(dim3(grid), dim3(block), smem, [&]() { kern(args...); });
+    return cudaSuccess;
+#else
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, block, smem, stream>>>(args...);
+    return cudaGetLastError();
+#endif
+}
+
+}  // namespace se

@@ -1,0 +1,168 @@
+"""Build + load the EMULATED C-ABI library (host pointers, fibers instead of CUDA threads).
+
+Test infrastructure only: lets the build container (no GPU) run the real kernel sources on tiny
+inputs and compare against the oracle.  The product package never imports this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "speech_enhancement_pytorch_b200", "csrc")
+BUILD = os.path.join(HERE, "_build")
+LIB = os.path.join(BUILD, "libse_b200_emu.so")
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+        os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"),
+        os.path.join(ROOT, "include", "se_b200.h")]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False):
+    if not (force or _stale()):
+        return LIB
+    os.makedirs(BUILD, exist_ok=True)
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-DSE_EMULATE", "-x", "c++", os.path.join(CSRC, "se_capi.cu"),
+           "-x", "c++", os.path.join(HERE, "cuda_emu.cpp"), "-I", HERE, "-I", CSRC,
+           "-shared", "-fPIC", "-o", LIB]
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.se_last_error.restype = ctypes.c_char_p
+        _lib.se_mrstft_workspace_bytes.restype = ctypes.c_int64
+        _lib.se_mrstft_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    return _lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"se error {rc}: {lib().se_last_error().decode()}")
+
+
+i64 = ctypes.c_int64
+f32 = ctypes.c_float
+ci = ctypes.c_int
+
+
+def stft_fwd(x, n, hop, win, scale):
+    rows, N = x.shape
+    T = 1 + N // hop
+    out = np.full((rows, n // 2 + 1, T, 2), np.nan, np.float32)
+    check(lib().se_stft_fwd(ptr(x), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win), f32(scale), None))
+    return out
+
+
+def stft_bwd(g, N, n, hop, win, scale, accumulate=False, init=None):
+    rows = g.shape[0]
+    out = np.full((rows, N), np.nan, np.float32) if init is None else init.copy()
+    check(lib().se_stft_bwd(ptr(g), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win), f32(scale),
+                            ci(int(accumulate)), None))
+    return out
+
+
+def istft_fwd(spec, length, n, hop, win, scale):
+    rows, F, T, _ = spec.shape
+    out = np.full((rows, length), np.nan, np.float32)
+    check(lib().se_istft_fwd(ptr(spec), ptr(out), i64(rows), i64(T), i64(length), ci(n), ci(hop), ci(win),
+                             f32(scale), None))
+    return out
+
+
+def istft_bwd(gy, T, n, hop, win, scale):
+    rows, length = gy.shape
+    out = np.full((rows, n // 2 + 1, T, 2), np.nan, np.float32)
+    check(lib().se_istft_bwd(ptr(gy), ptr(out), i64(rows), i64(T), i64(length), ci(n), ci(hop), ci(win),
+                             f32(scale), None))
+    return out
+
+
+def mask_fwd(spec, mask, mode, pre_tanh):
+    out = np.full(spec.shape, np.nan, np.float32)
+    check(lib().se_mask_fwd(ptr(spec), ptr(mask), ptr(out), i64(spec.size // 2), ci(mode), ci(int(pre_tanh)), None))
+    return out
+
+
+def mask_bwd(spec, mask, gout, mode, pre_tanh, want_gspec=True):
+    gm = np.full(mask.shape, np.nan, np.float32)
+    gs = np.full(spec.shape, np.nan, np.float32) if want_gspec else None
+    check(lib().se_mask_bwd(ptr(spec), ptr(mask), ptr(gout), ptr(gm), ptr(gs) if want_gspec else None,
+                            i64(spec.size // 2), ci(mode), ci(int(pre_tanh)), None))
+    return gm, gs
+
+
+def mrstft_fwd(est, ref):
+    rows, N = est.shape
+    ws = np.zeros(lib().se_mrstft_workspace_bytes(rows, N) // 8 + 1, np.float64)
+    sums = np.full(9, np.nan, np.float64)
+    check(lib().se_mrstft_loss_fwd(ptr(est), ptr(ref), i64(rows), i64(N), ptr(sums), ptr(ws), None))
+    loss = np.full(1, np.nan, np.float32)
+    check(lib().se_mrstft_loss_value(ptr(sums), i64(rows), i64(N), ptr(loss), None))
+    return sums, float(loss[0])
+
+
+def mrstft_bwd(est, ref, sums, gout=1.0):
+    rows, N = est.shape
+    g = np.full((rows, N), np.nan, np.float32)
+    go = np.array([gout], np.float32)
+    check(lib().se_mrstft_loss_bwd(ptr(est), ptr(ref), ptr(sums), ptr(go), i64(rows), i64(rows), i64(N), ptr(g), None))
+    return g
+
+
+def conv_stft_fwd(x, win_len, win_inc, fft_len):
+    rows, N = x.shape
+    T = (N + 2 * (win_len - win_inc) - win_len) // win_inc + 1
+    out = np.full((rows, 2 * (fft_len // 2 + 1), T), np.nan, np.float32)
+    check(lib().se_conv_stft_fwd(ptr(x), ptr(out), i64(rows), i64(N), ci(win_len), ci(win_inc), ci(fft_len), None))
+    return out
+
+
+def conv_istft_fwd(spec, out_len, win_len, win_inc, fft_len):
+    rows, _, T = spec.shape
+    out = np.full((rows, out_len), np.nan, np.float32)
+    check(lib().se_conv_istft_fwd(ptr(spec), ptr(out), i64(rows), i64(T), i64(out_len), ci(win_len), ci(win_inc),
+                                  ci(fft_len), None))
+    return out
+
+
+def conv_istft_bwd(gy, T, win_len, win_inc, fft_len):
+    rows, out_len = gy.shape
+    out = np.full((rows, 2 * (fft_len // 2 + 1), T), np.nan, np.float32)
+    check(lib().se_conv_istft_bwd(ptr(gy), ptr(out), i64(rows), i64(T), i64(out_len), ci(win_len), ci(win_inc),
+                                  ci(fft_len), None))
+    return out
+
+
+def enhance_fwd(x, mask, n, hop, win, mode, pre_tanh):
+    rows, N = x.shape
+    out = np.full((rows, N), np.nan, np.float32)
+    check(lib().se_enhance_fwd(ptr(x), ptr(mask), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win), ci(mode),
+                               ci(int(pre_tanh)), None))
+    return out
+
+
+def enhance_bwd(gy, x, mask, n, hop, win, mode, pre_tanh):
+    rows, N = x.shape
+    out = np.full(mask.shape, np.nan, np.float32)
+    check(lib().se_enhance_bwd(ptr(gy), ptr(x), ptr(mask), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win),
+                               ci(mode), ci(int(pre_tanh)), None))
+    return out
