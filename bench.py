@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the spectral hot path (BASELINE.json metric).
+
+One "step" = one pass of the whole path over one synthetic batch, BASELINE config[1]:
+  mixture [64,1,64000] (16 kHz, 4 s) -> STFT (n_fft 1024, hop 256, Hann) -> DCUnet complex-ratio
+  mask (polar 'E', tanh-squashed raw mask) -> iSTFT -> multi-resolution STFT loss (512/1024/2048)
+  vs the clean target -> backward to the raw mask.
+metric = audio-seconds processed per second (clips * N / 16000 per step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]        ours (one process per GPU)
+  python bench.py --impl reference ...                        the reference's CPU path (oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 16000
+N_FFT, HOP, WIN = 1024, 256, 1024
+RES = ((512, 128), (1024, 256), (2048, 512))
+METRIC = "audio-sec/s STFT+mask+iSTFT+MR-STFT loss fwd+bwd"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=64, help="utterances per GPU per step")
+    ap.add_argument("--nsample", type=int, default=64000)
+    ap.add_argument("--cpu-rows", type=int, default=16, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel timing loops (for ncu runs)")
+    ap.add_argument("--fused", type=int, default=-1, help="1: fused enhance kernels, 0: unfused, -1: auto")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": f"cfg2: DCUnet 'E' complex-ratio mask, n_fft={N_FFT} hop={HOP} Hann, "
+                        f"{args.rows}x{args.nsample / SR:g} s @16 kHz per GPU, MR-STFT loss 512/1024/2048, fwd+bwd to the raw mask",
+            "rows_per_gpu": args.rows, "nsample": args.nsample, "n_fft": N_FFT, "hop": HOP,
+            "global_rows": args.rows * world, "parallelism": f"utterance-sharded x{world}",
+            "l2": "working set ~400 MB/step > 126 MB L2; inputs rotate over 2 buffer sets"}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_chain(rows, nsample, steps, warmup, threads=None):
+    """The reference's own CPU implementation of the step (oracle port: same torch entry points the
+    reference calls, src/evaluate.py:101-162 + dcunet.py:131-161 + SURVEY 8c loss), timed on host cores."""
+    import types
+    import torch
+    from oracle import spectral_oracle as oref
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = types.SimpleNamespace(n_fft=N_FFT, hop_length=HOP, win_length=WIN, center=True)
+    g = torch.Generator().manual_seed(1235)
+    x = torch.randn(rows, 1, nsample, generator=g)
+    clean = x + 0.3 * torch.randn(rows, 1, nsample, generator=g)
+    raw = torch.randn(rows, 1, N_FFT // 2 + 1, 1 + nsample // HOP, 2, generator=g).requires_grad_(True)
+
+    def step():
+        spec = oref.stft_custom_ref(x, cfg)
+        y = oref.istft_custom_ref(oref.mask_apply_ref(spec, raw, "E", True), nsample, cfg)
+        loss = oref.mrstft_loss_ref(y, clean)
+        (graw,) = torch.autograd.grad(loss, raw)
+        return float(loss.detach()), graw
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rows = min(args.cpu_rows, args.rows)
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 2))
+    dt, threads = cpu_chain(rows, args.nsample, steps, warmup)
+    value = rows * args.nsample / SR / dt
+    sample = f"{rows} of {args.rows} rows per step, {steps} timed steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import speech_enhancement_pytorch_b200 as se
+    from speech_enhancement_pytorch_b200 import _native as nv
+    from speech_enhancement_pytorch_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    L = nv.lib()
+    rows, N = args.rows, args.nsample
+    F, T = N_FFT // 2 + 1, 1 + N // HOP
+    use_fused = args.fused == 1 or (args.fused == -1 and os.environ.get("SE_BENCH_FUSED", "0") == "1")
+
+    # ---- device-resident inputs (2 rotating sets) and preallocated intermediates
+    g = torch.Generator(device="cpu").manual_seed(1235 + rank)
+    sets = []
+    for _ in range(2):
+        x = torch.randn(rows, N, generator=g)
+        clean = x + 0.3 * torch.randn(rows, N, generator=g)
+        raw = torch.randn(rows, F, T, 2, generator=g)
+        sets.append((x.to(dev), clean.to(dev), raw.to(dev)))
+    X = torch.empty(rows, F, T, 2, device=dev)
+    Y = torch.empty_like(X)
+    y = torch.empty(rows, N, device=dev)
+    gy = torch.empty(rows, N, device=dev)
+    gY = torch.empty_like(X)
+    graw = torch.empty_like(X)
+    ws = torch.empty(max(int(L.se_mrstft_workspace_bytes(rows, N)), 8), dtype=torch.uint8, device=dev)
+    sums = torch.empty(9, dtype=torch.float64, device=dev)
+    loss = torch.empty((), device=dev)
+    one = torch.ones((), device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    P = lambda t: t.data_ptr()
+    count = rows * F * T
+    launches = {"n": 0}
+
+    def k_stft(x): nv.check(L.se_stft_fwd(P(x), P(X), rows, N, N_FFT, HOP, WIN, 1.0 / WIN, st))
+    def k_mask(raw): nv.check(L.se_mask_fwd(P(X), P(raw), P(Y), count, 1, 1, st))
+    def k_istft(): nv.check(L.se_istft_fwd(P(Y), P(y), rows, T, N, N_FFT, HOP, WIN, float(WIN), st))
+    def k_loss_fwd(clean): nv.check(L.se_mrstft_loss_fwd(P(y), P(clean), rows, N, P(sums), P(ws), st))
+    def k_loss_val(): nv.check(L.se_mrstft_loss_value(P(sums), rows * world, N, P(loss), st))
+    def k_loss_bwd(clean): nv.check(L.se_mrstft_loss_bwd(P(y), P(clean), P(sums), P(one), rows * world, rows, N, P(gy), st))
+    def k_istft_bwd(): nv.check(L.se_istft_bwd(P(gy), P(gY), rows, T, N, N_FFT, HOP, WIN, float(WIN), st))
+    def k_mask_bwd(raw): nv.check(L.se_mask_bwd(P(X), P(raw), P(gY), P(graw), 0, count, 1, 1, st))
+    def k_enh_fwd(x, raw): nv.check(L.se_enhance_fwd(P(x), P(raw), P(y), rows, N, N_FFT, HOP, WIN, 1, 1, st))
+    def k_enh_bwd(x, raw): nv.check(L.se_enhance_bwd(P(gy), P(x), P(raw), P(graw), rows, N, N_FFT, HOP, WIN, 1, 1, st))
+
+    def step(i):
+        x, clean, raw = sets[i & 1]
+        if use_fused:
+            k_enh_fwd(x, raw)
+        else:
+            k_stft(x); k_mask(raw); k_istft()
+        k_loss_fwd(clean)
+        if group is not None:
+            dist.all_reduce(sums, group=group)          # the path's only exchange step
+        k_loss_val()
+        k_loss_bwd(clean)
+        if use_fused:
+            k_enh_bwd(x, raw)
+        else:
+            k_istft_bwd(); k_mask_bwd(raw)
+
+    n_launch = (2 if use_fused else 5) + 6 + 1 + 3      # + 3 loss fwd, 3 reduce, value, 3 loss bwd
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if group is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if group is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    audio_s = rows * world * N / SR
+    value = audio_s / (ms_per_step * 1e-3)
+    loss_val = float(loss)
+
+    # ---- per-kernel breakdown (CUDA events on the launching stream), rank 0 only
+    kernels = []
+    if rank == 0 and not args.no_breakdown:
+        S_, P_, M_ = 4.0 * N, 8.0 * F * T, 8.0 * F * T
+        flop_fft = lambda n, h: 2.5 * n * (n.bit_length() - 1) * (1 + N // h)
+        f1024 = flop_fft(N_FFT, HOP)
+        f_all = sum(flop_fft(n, h) for n, h in RES)
+        table = [
+            ("stft_fwd", lambda i: k_stft(sets[i & 1][0]), S_ + P_, f1024, 1),
+            ("mask_fwd", lambda i: k_mask(sets[i & 1][2]), 2 * P_ + M_, 0, 1),
+            ("istft_fwd", lambda i: k_istft(), P_ + S_, f1024, 1),
+            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 3 * 2 * S_, 2 * f_all, 6),
+            ("mrstft_loss_bwd(3 res)", lambda i: k_loss_bwd(sets[i & 1][1]), 3 * 3 * S_, 3 * f_all, 3),
+            ("istft_bwd", lambda i: k_istft_bwd(), S_ + P_, f1024, 1),
+            ("mask_bwd", lambda i: k_mask_bwd(sets[i & 1][2]), 2 * P_ + 2 * M_, 0, 1),
+        ]
+        if use_fused:
+            table += [("enhance_fwd", lambda i: k_enh_fwd(sets[i & 1][0], sets[i & 1][2]), 2 * S_ + M_, 2 * f1024, 1),
+                      ("enhance_bwd", lambda i: k_enh_bwd(sets[i & 1][0], sets[i & 1][2]), 2 * S_ + 2 * M_, 2 * f1024, 1)]
+        reps = 20
+        for name, fn, bytes_row, flops_row, nl in table:
+            for i in range(3):
+                fn(i)
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(reps):
+                fn(i)
+            b.record()
+            torch.cuda.synchronize(dev)
+            us = a.elapsed_time(b) * 1e3 / reps
+            kernels.append({"name": name, "us": round(us, 2), "launches": nl,
+                            "alg_bytes": bytes_row * rows, "gbs": round(bytes_row * rows / us * 1e-3, 1),
+                            "tflops_fp32": round(flops_row * rows / us * 1e-6, 2)})
+
+    # ---- end-to-end through the public API with host buffers (pinned), copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        import types
+        cfg = types.SimpleNamespace(n_fft=N_FFT, hop_length=HOP, win_length=WIN, center=True)
+        hx = [torch.randn(rows, 1, N, generator=g).pin_memory() for _ in range(2)]
+        hc = [(hx[i] + 0.3 * torch.randn(rows, 1, N, generator=g)).pin_memory() for i in range(2)]
+        hm = [torch.randn(rows, 1, F, T, 2, generator=g).pin_memory() for _ in range(2)]
+        hloss = torch.empty((), pin_memory=True)
+        copy_stream = torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        dbuf = [(torch.empty(rows, 1, N, device=dev), torch.empty(rows, 1, N, device=dev),
+                 torch.empty(rows, 1, F, T, 2, device=dev)) for _ in range(2)]
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def upload(i):
+            j = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[j])
+                dbuf[j][0].copy_(hx[j], non_blocking=True)
+                dbuf[j][1].copy_(hc[j], non_blocking=True)
+                dbuf[j][2].copy_(hm[j], non_blocking=True)
+                ready[j].record(copy_stream)
+
+        def e2e_step(i):
+            j = i & 1
+            main.wait_event(ready[j])
+            x, clean = dbuf[j][0], dbuf[j][1]
+            raw = dbuf[j][2].detach().requires_grad_(True)
+            if use_fused:
+                yy = se.enhance(x, raw, cfg, "E", True)
+            else:
+                yy = se.istft_custom(se.apply_mask(se.stft_custom(x, cfg), raw, "E", True), N, cfg)
+            l = se.loss_mrstft(yy, clean, group)
+            l.backward()
+            hloss.copy_(l.detach(), non_blocking=True)
+            consumed[j].record(main)
+            return raw.grad
+
+        for j in range(2):
+            consumed[j].record(main)
+        e2e_steps = max(5, min(args.steps, 30))
+        upload(0)
+        for i in range(3):
+            upload(i + 1)
+            e2e_step(i)
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        upload(3)
+        a.record()
+        for i in range(3, 3 + e2e_steps):
+            upload(i + 1)
+            e2e_step(i)
+        b.record()
+        sync_all()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if group is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t) / e2e_steps
+        h2d = (hx[0].numel() + hc[0].numel() + hm[0].numel()) * 4
+        e2e = {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+               "api": "stft_custom/apply_mask/istft_custom/loss_mrstft + autograd; pinned host inputs, copy stream double-buffered",
+               "loss": float(hloss)}
+
+    if rank != 0:
+        if group is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    in_step = [k for k in kernels if k["name"].startswith("mrstft") or
+               (use_fused and k["name"].startswith("enhance")) or
+               (not use_fused and not k["name"].startswith("enhance"))]
+    dom = max(in_step, key=lambda k: k["us"]) if in_step else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom["name"])
+    except Exception:
+        pass
+    fp32_peak = 148 * 128 * 2 * (float(clocks["sm_max_mhz"]) if clocks and clocks.get("sm_max_mhz") else 1965.0) * 1e-6
+    roofline = None
+    if dom:
+        per_launch_bytes = dom["alg_bytes"] / dom["launches"]
+        per_launch_us = dom["us"] / dom["launches"]
+        roofline = {"kernel": dom["name"], "bound": "hbm", "achieved": round(per_launch_bytes / per_launch_us * 1e-3, 1),
+                    "peak": hbm_peak, "unit": "GB/s", "frac": round(per_launch_bytes / per_launch_us * 1e-3 / hbm_peak, 4),
+                    "traffic": traffic, "peak_source": peak_src,
+                    "share_of_step": round(dom["us"] / sum(k["us"] for k in in_step), 3),
+                    "fp32": {"achieved_tflops": dom["tflops_fp32"], "peak_tflops": round(fp32_peak, 1),
+                             "frac": round(dom["tflops_fp32"] / fp32_peak, 4),
+                             "note": "MR-STFT loss is fp32-pipe bound (~75 flop/B, SURVEY 8d); flops = 2.5 n log2 n per frame"}}
+        for k in kernels:
+            k["hbm_frac"] = round(k["gbs"] / hbm_peak, 4)
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        crow = min(args.cpu_rows, rows)
+        dt, threads = cpu_chain(crow, N, 3, 1)
+        cpu_baseline = {"value": crow * N / SR / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{crow} of {rows} rows per step, 3 timed steps ({dt * 1e3:.0f} ms/step), torch CPU oracle"}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
+        "fused": use_fused, "loss": loss_val, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+    }))
+    if group is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,23 @@
+"""speech_enhancement_pytorch_b200 -- B200-native (sm_100a) spectral front/back-end behind the
+call signatures of ooshyun/Speech-Enhancement-Pytorch's hot path.
+
+(The task names the package `speech-enhancement-pytorch_b200`; a hyphen is not importable, so
+the directory uses underscores.)
+
+Public surface (all CUDA-only, no CPU fallback):
+    stft_custom, istft_custom          src/evaluate.py:101-162
+    apply_mask, apply_mask_dccrn       model forward tails
+    loss_mrstft, MRSTFTLoss            loss_function(enhanced, sources) convention
+    ConvSTFT, ConviSTFT                src/model/dccrn.py:669-747
+    enhance                            fused stft_custom -> mask -> istft_custom
+"""
+from .evaluate import stft_custom, istft_custom
+from .masking import apply_mask, apply_mask_dccrn
+from .loss import loss_mrstft, MRSTFTLoss
+from .dccrn import ConvSTFT, ConviSTFT
+from .fused import enhance
+from . import _native
+
+__all__ = ["stft_custom", "istft_custom", "apply_mask", "apply_mask_dccrn", "loss_mrstft", "MRSTFTLoss",
+           "ConvSTFT", "ConviSTFT", "enhance"]
+__version__ = "0.1.0"

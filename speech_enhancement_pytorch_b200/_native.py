@@ -1,0 +1,138 @@
+"""ctypes binding of libse_b200.so (the C-ABI in include/se_b200.h).
+
+There is NO fallback: if the library is missing or the tensors are not CUDA fp32, the calls
+raise.  PyTorch is used only for device memory, streams and autograd plumbing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libse_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+EXPORTS = (
+    "se_version", "se_last_error", "se_stft_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
+    "se_mask_fwd", "se_mask_bwd", "se_mrstft_workspace_bytes", "se_mrstft_loss_fwd",
+    "se_mrstft_loss_value", "se_mrstft_loss_bwd", "se_enhance_fwd", "se_enhance_bwd",
+    "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
+)
+
+MASK_MODES = {"real": 0, "E": 1, "C": 2, "R": 3}
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = _sources() + [os.path.join(_ROOT, "include", "se_b200.h")]
+    return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/se_capi.cu for sm_100a with nvcc into the in-tree libse_b200.so."""
+    if not (force or needs_build()):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB_PATH, os.path.join(CSRC, "se_capi.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+_c = ctypes
+_I64, _INT, _F32, _PTR = _c.c_int64, _c.c_int, _c.c_float, _c.c_void_p
+
+
+def lib():
+    """Load (once) and return the C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+            L = ctypes.CDLL(LIB_PATH)
+            L.se_last_error.restype = _c.c_char_p
+            L.se_mrstft_workspace_bytes.restype = _I64
+            L.se_mrstft_workspace_bytes.argtypes = [_I64, _I64]
+            L.se_stft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
+            L.se_stft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _PTR]
+            L.se_istft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
+            L.se_istft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
+            L.se_mask_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _INT, _INT, _PTR]
+            L.se_mask_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _I64, _INT, _INT, _PTR]
+            L.se_mrstft_loss_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _PTR, _PTR, _PTR]
+            L.se_mrstft_loss_value.argtypes = [_PTR, _I64, _I64, _PTR, _PTR]
+            L.se_mrstft_loss_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _PTR, _PTR]
+            L.se_enhance_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
+            L.se_enhance_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
+            L.se_conv_stft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _PTR]
+            L.se_conv_istft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]
+            L.se_conv_istft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]
+            _lib = L
+    return _lib
+
+
+class SEError(RuntimeError):
+    pass
+
+
+_ERR = {-1: ValueError, -2: NotImplementedError, -3: SEError, -4: RuntimeError}
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().se_last_error().decode()
+        raise _ERR.get(rc, SEError)(f"se_b200[{rc}]: {msg}")
+
+
+def require_cuda_f32(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("speech_enhancement_pytorch_b200 runs on CUDA tensors only "
+                               "(hand-written sm_100a kernels; there is no CPU fallback)")
+        if t.dtype != torch.float32:
+            raise TypeError(f"expected float32 tensors, got {t.dtype}")
+        if not t.is_contiguous():
+            raise ValueError("internal error: tensor must be contiguous at the C-ABI")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """Make `device` current around a C-ABI call (tables are cached per current device)."""
+
+    def __init__(self, device):
+        self.guard = torch.cuda.device(device)
+
+    def __enter__(self):
+        self.guard.__enter__()
+
+    def __exit__(self, *a):
+        return self.guard.__exit__(*a)

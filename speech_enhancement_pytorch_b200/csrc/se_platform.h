@@ -16,6 +16,9 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace se {
 
@@ -28,8 +31,19 @@ inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block
     return cudaSuccess;
 #else
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        // opt in to large dynamic shared memory once per (device, kernel); keeps the steady-state
+        // launch path free of driver calls (and CUDA-graph capturable)
+        static std::mutex mu;
+        static std::set<std::pair<int, const void*>> done;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_pair(dev, reinterpret_cast<const void*>(kern));
+        if (!done.count(key)) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            done.insert(key);
+        }
     }
     kern<<<grid, block, smem, stream>>>(args...);
     return cudaGetLastError();

@@ -1,0 +1,28 @@
+"""Mask application as one fused op (the tails of the reference models' `forward`s):
+
+  'real'  unet.py:62, dnn.py:140, stft_rnn.py:108-109, mel_rnn.py:113, crn.py:139-141
+  'E'     dcunet.py:136-155, dccrn.py:203-217  (polar; 1e-8 placements kept)
+  'C'     dcunet.py:156-157, dccrn.py:218-219
+  'R'     dcunet.py:158-159, dccrn.py:220-221
+  pre_tanh=True squashes the raw mask first (dcunet.py:131).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def apply_mask(spec, mask, mode="E", pre_tanh=False):
+    """spec [...,F,T,2]; mask [...,F,T] for 'real', [...,F,T,2] otherwise -> [...,F,T,2]."""
+    return ops.mask_apply(spec, mask, mode, pre_tanh)
+
+
+def apply_mask_dccrn(specs, mask_real, mask_imag, mode="E"):
+    """DCCRN layout (dccrn.py:147-223): specs [B,2F,T] (Re bins then Im bins), masks [B,F,T];
+    returns out_spec [B,2F,T]."""
+    nf = specs.shape[1] // 2
+    spec = torch.stack([specs[:, :nf], specs[:, nf:]], dim=-1)
+    mask = torch.stack([mask_real, mask_imag], dim=-1)
+    out = ops.mask_apply(spec, mask, mode, False)
+    return torch.cat([out[..., 0], out[..., 1]], dim=1)

@@ -1,0 +1,260 @@
+"""Row-level ops over the C-ABI, with autograd.  Shapes are already flattened to rows here;
+the reference-facing signatures live in evaluate.py / masking.py / loss.py / dccrn.py.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _native as nv
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _check_cfg(n_fft, hop, win_length):
+    if n_fft not in (512, 1024, 2048):
+        raise NotImplementedError(f"n_fft={n_fft}: only 512/1024/2048 are built (no fallback path)")
+    if hop * 4 != n_fft and hop * 2 != n_fft:
+        raise NotImplementedError(f"hop_length={hop}: only n_fft/4 and n_fft/2 are built")
+    if not (2 <= win_length <= n_fft):
+        raise NotImplementedError(f"win_length={win_length} must be in [2, n_fft]")
+
+
+# ------------------------------------------------------------------ raw calls
+def stft_rows(x, n_fft, hop, win_length, scale):
+    nv.require_cuda_f32(x)
+    rows, n = x.shape
+    out = torch.empty((rows, n_fft // 2 + 1, 1 + n // hop, 2), dtype=torch.float32, device=x.device)
+    with nv.on_device(x.device):
+        nv.check(nv.lib().se_stft_fwd(x.data_ptr(), out.data_ptr(), rows, n, n_fft, hop, win_length, scale,
+                                      nv.stream_ptr(x.device)))
+    return out
+
+
+def stft_rows_adjoint(g, nsample, n_fft, hop, win_length, scale, out=None):
+    nv.require_cuda_f32(g, out)
+    rows = g.shape[0]
+    acc = out is not None
+    if out is None:
+        out = torch.empty((rows, nsample), dtype=torch.float32, device=g.device)
+    with nv.on_device(g.device):
+        nv.check(nv.lib().se_stft_bwd(g.data_ptr(), out.data_ptr(), rows, nsample, n_fft, hop, win_length, scale,
+                                      int(acc), nv.stream_ptr(g.device)))
+    return out
+
+
+def istft_rows(spec, length, n_fft, hop, win_length, scale):
+    nv.require_cuda_f32(spec)
+    rows, nf, nt, _ = spec.shape
+    out = torch.empty((rows, length), dtype=torch.float32, device=spec.device)
+    with nv.on_device(spec.device):
+        nv.check(nv.lib().se_istft_fwd(spec.data_ptr(), out.data_ptr(), rows, nt, length, n_fft, hop, win_length,
+                                       scale, nv.stream_ptr(spec.device)))
+    return out
+
+
+def istft_rows_adjoint(gy, nframe, n_fft, hop, win_length, scale):
+    nv.require_cuda_f32(gy)
+    rows, length = gy.shape
+    out = torch.empty((rows, n_fft // 2 + 1, nframe, 2), dtype=torch.float32, device=gy.device)
+    with nv.on_device(gy.device):
+        nv.check(nv.lib().se_istft_bwd(gy.data_ptr(), out.data_ptr(), rows, nframe, length, n_fft, hop, win_length,
+                                       scale, nv.stream_ptr(gy.device)))
+    return out
+
+
+# ------------------------------------------------------------------ autograd
+class _STFT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n_fft, hop, win_length, scale):
+        ctx.cfg = (x.shape[1], n_fft, hop, win_length, scale)
+        return stft_rows(x, n_fft, hop, win_length, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        n, n_fft, hop, win_length, scale = ctx.cfg
+        return stft_rows_adjoint(g.contiguous(), n, n_fft, hop, win_length, scale), None, None, None, None
+
+
+class _ISTFT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, length, n_fft, hop, win_length, scale):
+        ctx.cfg = (spec.shape[2], n_fft, hop, win_length, scale)
+        return istft_rows(spec, length, n_fft, hop, win_length, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        nt, n_fft, hop, win_length, scale = ctx.cfg
+        return istft_rows_adjoint(g.contiguous(), nt, n_fft, hop, win_length, scale), None, None, None, None, None
+
+
+def _as_f32(t):
+    if t.dtype in (torch.float16, torch.bfloat16):
+        return t.float()          # spectra stay fp32 under a bf16/fp16 model (BASELINE config 4)
+    return t
+
+
+def stft(x_rows, n_fft, hop, win_length, scale):
+    _check_cfg(n_fft, hop, win_length)
+    return _STFT.apply(_as_f32(x_rows).contiguous(), n_fft, hop, win_length, float(scale))
+
+
+def istft(spec_rows, length, n_fft, hop, win_length, scale):
+    _check_cfg(n_fft, hop, win_length)
+    return _ISTFT.apply(_as_f32(spec_rows).contiguous(), int(length), n_fft, hop, win_length, float(scale))
+
+
+class _Mask(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, mask, mode, pre_tanh):
+        nv.require_cuda_f32(spec, mask)
+        out = torch.empty_like(spec)
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_mask_fwd(spec.data_ptr(), mask.data_ptr(), out.data_ptr(), spec.numel() // 2,
+                                          mode, int(pre_tanh), nv.stream_ptr(spec.device)))
+        ctx.save_for_backward(spec, mask)
+        ctx.cfg = (mode, pre_tanh)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        spec, mask = ctx.saved_tensors
+        mode, pre_tanh = ctx.cfg
+        g = g.contiguous()
+        gmask = torch.empty_like(mask)
+        gspec = torch.empty_like(spec) if ctx.needs_input_grad[0] else None
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_mask_bwd(spec.data_ptr(), mask.data_ptr(), g.data_ptr(), gmask.data_ptr(),
+                                          _ptr(gspec), spec.numel() // 2, mode, int(pre_tanh),
+                                          nv.stream_ptr(spec.device)))
+        return gspec, gmask, None, None
+
+
+def mask_apply(spec, mask, mode, pre_tanh=False):
+    """spec [...,2], mask [...] ('real') or [...,2]; returns a tensor shaped like spec."""
+    if mode not in nv.MASK_MODES:
+        raise ValueError(f"unknown masking mode {mode!r}")
+    want = spec.shape[:-1] if mode == "real" else spec.shape
+    if tuple(mask.shape) != tuple(want):
+        raise ValueError(f"mask shape {tuple(mask.shape)} does not match spectrum {tuple(spec.shape)} for mode {mode}")
+    return _Mask.apply(_as_f32(spec).contiguous(), _as_f32(mask).contiguous(), nv.MASK_MODES[mode], bool(pre_tanh))
+
+
+class _MRSTFT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, est, ref, group, global_rows_hint):
+        nv.require_cuda_f32(est, ref)
+        rows, n = est.shape
+        L = nv.lib()
+        ws = torch.empty(max(int(L.se_mrstft_workspace_bytes(rows, n)), 8), dtype=torch.uint8, device=est.device)
+        sums = torch.empty(9, dtype=torch.float64, device=est.device)
+        loss = torch.empty((), dtype=torch.float32, device=est.device)
+        global_rows = rows
+        with nv.on_device(est.device):
+            st = nv.stream_ptr(est.device)
+            nv.check(L.se_mrstft_loss_fwd(est.data_ptr(), ref.data_ptr(), rows, n, sums.data_ptr(), ws.data_ptr(), st))
+            if group is not None:
+                import torch.distributed as dist
+                # the one exchange step of the path: 9 partial sums, no host sync.
+                # Utterance sharding gives every rank the same row count unless told otherwise.
+                dist.all_reduce(sums, group=group)
+                global_rows = global_rows_hint or rows * dist.get_world_size(group)
+            nv.check(L.se_mrstft_loss_value(sums.data_ptr(), global_rows, n, loss.data_ptr(), st))
+        ctx.save_for_backward(est, ref, sums)
+        ctx.global_rows = global_rows
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        est, ref, sums = ctx.saved_tensors
+        rows, n = est.shape
+        gout = gout.contiguous().float()
+        g = torch.empty_like(est)
+        with nv.on_device(est.device):
+            nv.check(nv.lib().se_mrstft_loss_bwd(est.data_ptr(), ref.data_ptr(), sums.data_ptr(), gout.data_ptr(),
+                                                 ctx.global_rows, rows, n, g.data_ptr(), nv.stream_ptr(est.device)))
+        return g, None, None, None
+
+
+def mrstft_loss_rows(est_rows, ref_rows, group=None, global_rows=None):
+    if ref_rows.requires_grad:
+        raise NotImplementedError("loss_mrstft: gradient flows to `enhanced` only (targets must not require grad)")
+    return _MRSTFT.apply(_as_f32(est_rows).contiguous(), _as_f32(ref_rows).contiguous(), group, global_rows)
+
+
+# ------------------------------------------------------------------ fused enhance
+class _Enhance(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, n_fft, hop, win_length, mode, pre_tanh):
+        nv.require_cuda_f32(x, mask)
+        rows, n = x.shape
+        y = torch.empty_like(x)
+        with nv.on_device(x.device):
+            nv.check(nv.lib().se_enhance_fwd(x.data_ptr(), mask.data_ptr(), y.data_ptr(), rows, n, n_fft, hop,
+                                             win_length, mode, int(pre_tanh), nv.stream_ptr(x.device)))
+        ctx.save_for_backward(x, mask)
+        ctx.cfg = (n_fft, hop, win_length, mode, pre_tanh)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mask = ctx.saved_tensors
+        n_fft, hop, win_length, mode, pre_tanh = ctx.cfg
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("enhance: gradient wrt the input waveform is not built")
+        rows, n = x.shape
+        gy = gy.contiguous()
+        gmask = torch.empty_like(mask)
+        with nv.on_device(x.device):
+            nv.check(nv.lib().se_enhance_bwd(gy.data_ptr(), x.data_ptr(), mask.data_ptr(), gmask.data_ptr(), rows, n,
+                                             n_fft, hop, win_length, mode, int(pre_tanh), nv.stream_ptr(x.device)))
+        return None, gmask, None, None, None, None, None
+
+
+def enhance_rows(x_rows, mask_rows, n_fft, hop, win_length, mode, pre_tanh=False):
+    _check_cfg(n_fft, hop, win_length)
+    if mode not in nv.MASK_MODES:
+        raise ValueError(f"unknown masking mode {mode!r}")
+    return _Enhance.apply(_as_f32(x_rows).contiguous(), _as_f32(mask_rows).contiguous(), n_fft, hop, win_length,
+                          nv.MASK_MODES[mode], bool(pre_tanh))
+
+
+# ------------------------------------------------------------------ DCCRN conv transforms
+def conv_stft_rows(x, win_len, win_inc, fft_len):
+    nv.require_cuda_f32(x)
+    rows, n = x.shape
+    nt = (n + 2 * (win_len - win_inc) - win_len) // win_inc + 1
+    out = torch.empty((rows, 2 * (fft_len // 2 + 1), nt), dtype=torch.float32, device=x.device)
+    with nv.on_device(x.device):
+        nv.check(nv.lib().se_conv_stft_fwd(x.data_ptr(), out.data_ptr(), rows, n, win_len, win_inc, fft_len,
+                                           nv.stream_ptr(x.device)))
+    return out
+
+
+class _ConvISTFT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec, out_len, win_len, win_inc, fft_len):
+        nv.require_cuda_f32(spec)
+        rows, _, nt = spec.shape
+        y = torch.empty((rows, out_len), dtype=torch.float32, device=spec.device)
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_conv_istft_fwd(spec.data_ptr(), y.data_ptr(), rows, nt, out_len, win_len, win_inc,
+                                                fft_len, nv.stream_ptr(spec.device)))
+        ctx.cfg = (nt, win_len, win_inc, fft_len)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        nt, win_len, win_inc, fft_len = ctx.cfg
+        gy = gy.contiguous()
+        rows, out_len = gy.shape
+        g = torch.empty((rows, 2 * (fft_len // 2 + 1), nt), dtype=torch.float32, device=gy.device)
+        with nv.on_device(gy.device):
+            nv.check(nv.lib().se_conv_istft_bwd(gy.data_ptr(), g.data_ptr(), rows, nt, out_len, win_len, win_inc,
+                                                fft_len, nv.stream_ptr(gy.device)))
+        return g, None, None, None, None
+
+
+def conv_istft_rows(spec, out_len, win_len, win_inc, fft_len):
+    return _ConvISTFT.apply(_as_f32(spec).contiguous(), int(out_len), win_len, win_inc, fft_len)

@@ -1,0 +1,50 @@
+"""Host-side logic of the reference-facing API that can be checked without a GPU."""
+import types
+
+import pytest
+import torch
+
+import speech_enhancement_pytorch_b200 as se
+
+
+def cfg(n=512, h=128, w=512, center=True):
+    return types.SimpleNamespace(n_fft=n, hop_length=h, win_length=w, center=center)
+
+
+def test_cpu_tensors_are_refused_loudly():
+    x = torch.randn(1, 1, 4096)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.stft_custom(x, cfg())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.istft_custom(torch.randn(1, 1, 257, 33, 2), 4096, cfg())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.loss_mrstft(x, x.clone())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.apply_mask(torch.randn(1, 1, 257, 33, 2), torch.randn(1, 1, 257, 33, 2), "E")
+
+
+def test_unsupported_configs_raise_not_fallback():
+    x = torch.randn(1, 1, 4096)
+    with pytest.raises(NotImplementedError):
+        se.stft_custom(x, cfg(320, 80, 320))          # commented CRN setting, src/conf/config.yaml:78-80
+    with pytest.raises(NotImplementedError):
+        se.stft_custom(x, cfg(512, 100, 512))
+    with pytest.raises(NotImplementedError):
+        se.stft_custom(x, cfg(center=False))
+    with pytest.raises(ValueError):
+        se.stft_custom(torch.randn(4096), cfg())
+    with pytest.raises(ValueError):
+        se.istft_custom(torch.randn(257, 33, 2), 4096, cfg())
+    with pytest.raises(ValueError):
+        se.apply_mask(torch.randn(1, 1, 257, 33, 2), torch.randn(1, 1, 257, 33), "E")
+    with pytest.raises(ValueError):
+        se.apply_mask(torch.randn(1, 1, 257, 33, 2), torch.randn(1, 1, 257, 33, 2), "Z")
+    with pytest.raises(NotImplementedError):
+        se.ConvSTFT(400, 100, 512, "hamming")
+
+
+def test_modules_keep_reference_attributes():
+    st = se.ConvSTFT(400, 100, None, "hann", "complex")
+    assert (st.fft_len, st.stride, st.win_len, st.dim) == (512, 100, 400, 512)
+    ist = se.ConviSTFT(400, 100, 512, 16384, "hann", "complex")
+    assert (ist.length, ist.stride, ist.win_len) == (16384, 100, 400)

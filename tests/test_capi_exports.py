@@ -1,0 +1,50 @@
+"""The product library builds for sm_100a, loads, and exports every symbol include/se_b200.h
+declares (no compute calls: there is no GPU in the build container)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "se_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(se_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_and_python_binding_agree():
+    from speech_enhancement_pytorch_b200 import _native
+    assert sorted(_native.EXPORTS) == declared_symbols()
+
+
+def test_library_builds_and_exports_all_symbols():
+    from speech_enhancement_pytorch_b200 import _native
+    path = _native.build()
+    lib = ctypes.CDLL(path)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+    assert lib.se_version() >= 100
+
+
+def test_sass_is_sm100():
+    from speech_enhancement_pytorch_b200 import _native
+    import subprocess
+    path = _native.build()
+    out = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    from speech_enhancement_pytorch_b200 import _native
+    L = _native.lib()
+    assert L.se_stft_fwd(None, None, 1, 4096, 512, 128, 512, 1.0, None) == -1
+    assert b"null" in L.se_last_error()
+    buf = (ctypes.c_float * 4)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.se_stft_fwd(p, p, 1, 4096, 320, 80, 320, 1.0, None) == -2          # n_fft=320: clear error, no fallback
+    assert L.se_stft_fwd(p, p, 1, 4096, 512, 100, 512, 1.0, None) == -2
+    assert L.se_istft_fwd(p, p, 1, 0, 100, 512, 128, 512, 1.0, None) == -1
+    assert L.se_mask_fwd(p, p, p, 4, 7, 0, None) == -2

@@ -1,0 +1,141 @@
+"""Kernel sources run under the CUDA-semantics emulator (tests/cuda_emu) and compared with the
+oracle -- CPU-only debugging aid for index math (framing, reflect folds, OLA carries, chunking).
+The emulated library is test infrastructure; the product never loads it."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu"))
+import emu_lib as E  # noqa: E402
+from oracle import spectral_np64 as o64  # noqa: E402
+from oracle import spectral_oracle as oref  # noqa: E402
+from conftest import golden  # noqa: E402
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30)
+
+
+def c2(a):
+    return a[..., 0] + 1j * a[..., 1]
+
+
+def r2(c):
+    return np.ascontiguousarray(np.stack([c.real, c.imag], -1).astype(np.float32))
+
+
+CASES = [(512, 128, 512, 2085), (1024, 256, 1024, 4351), (2048, 512, 2048, 8705), (512, 256, 512, 3000),
+         (512, 128, 400, 2500), (1024, 512, 1024, 4100), (512, 128, 512, 9001)]
+
+
+@pytest.mark.parametrize("n,hop,win,N", CASES)
+def test_emu_transforms_vs_f64(n, hop, win, N):
+    rng = np.random.default_rng(n + N)
+    x = rng.standard_normal((2, N)).astype(np.float32)
+    T, F = 1 + N // hop, n // 2 + 1
+    s = E.stft_fwd(x, n, hop, win, 1.0 / win)
+    assert rel(c2(s), o64.stft(x, n, hop, win)) < 1e-6
+    spec = rng.standard_normal((2, F, T)) + 1j * rng.standard_normal((2, F, T))
+    for length in (N, N - 150, N + 100):
+        y = E.istft_fwd(r2(spec), length, n, hop, win, float(win))
+        assert not np.isnan(y).any()
+        assert rel(y, o64.istft(spec.astype(np.complex64), n, hop, win, length)) < 2e-6
+        gy = rng.standard_normal((2, length)).astype(np.float32)
+        gs = E.istft_bwd(gy, T, n, hop, win, float(win))
+        assert rel(c2(gs), o64.istft_adjoint(gy, T, n, hop, win)) < 2e-6
+    g = r2(spec)
+    gx = E.stft_bwd(g, N, n, hop, win, 1.0 / win)
+    assert not np.isnan(gx).any()
+    assert rel(gx, o64.stft_adjoint(c2(g), N, n, hop, win)) < 2e-6
+    base = rng.standard_normal((2, N)).astype(np.float32)
+    gx2 = E.stft_bwd(g, N, n, hop, win, 1.0 / win, accumulate=True, init=base)
+    assert rel(gx2 - base, gx) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["stft_n512", "stft_n1024", "stft_n2048", "stft_n512_hop256", "stft_n512_win400",
+                                  "stft_n512_short_len", "stft_n512_long_len", "stft_structured"])
+def test_emu_matches_reference_golden(name):
+    g = golden(name)
+    n, h, w, length = (int(v) for v in g["meta"])
+    x = np.ascontiguousarray(g["x"].reshape(-1, g["x"].shape[-1]))
+    spec = g["spec"].reshape(x.shape[0], n // 2 + 1, -1, 2)
+    s = E.stft_fwd(x, n, h, w, 1.0 / w)
+    assert rel(s, spec) < 1e-4                      # north_star: spectra within 1e-4 relative
+    assert np.abs(s - spec).max() < 2e-6
+    y = E.istft_fwd(np.ascontiguousarray(spec), length, n, h, w, float(w))
+    assert rel(y, g["y"].reshape(x.shape[0], -1)) < 1e-4
+    if "spec2" in g:
+        y2 = E.istft_fwd(np.ascontiguousarray(g["spec2"].reshape(spec.shape)), length, n, h, w, float(w))
+        assert rel(y2, g["y2"].reshape(x.shape[0], -1)) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["grad_n512", "grad_n1024", "grad_n512_win400"])
+def test_emu_adjoints_match_reference_autograd(name):
+    g = golden(name)
+    n, h, w, N = (int(v) for v in g["meta"])
+    rows = g["x"].shape[0] * g["x"].shape[1]
+    gx = E.stft_bwd(np.ascontiguousarray(g["gspec"].reshape(rows, n // 2 + 1, -1, 2)), N, n, h, w, 1.0 / w)
+    assert rel(gx, g["gx"].reshape(rows, N)) < 1e-5
+    T = g["s"].shape[-2]
+    gs = E.istft_bwd(np.ascontiguousarray(g["gy"].reshape(rows, N)), T, n, h, w, float(w))
+    assert rel(gs, g["gs"].reshape(rows, n // 2 + 1, T, 2)) < 1e-5
+
+
+@pytest.mark.parametrize("mode,name", [(0, "real"), (1, "E"), (2, "C"), (3, "R")])
+@pytest.mark.parametrize("pre_tanh", [False, True])
+def test_emu_masks(mode, name, pre_tanh):
+    rng = np.random.default_rng(mode)
+    spec = rng.standard_normal((2, 33, 7, 2)).astype(np.float32)
+    spec[0, 0, 0] = 0.0                                        # atan2(0,0) corner
+    m = rng.standard_normal((2, 33, 7) if mode == 0 else (2, 33, 7, 2)).astype(np.float32)
+    out = E.mask_fwd(spec, m, mode, pre_tanh)
+    st = torch.from_numpy(spec).double().requires_grad_(True)
+    mt = torch.from_numpy(m).double().requires_grad_(True)
+    o = oref.mask_apply_ref(st, mt, name, pre_tanh)
+    assert rel(out, o.detach().numpy()) < 1e-6
+    go = rng.standard_normal(spec.shape).astype(np.float32)
+    go[0, 0, 0] = 0.0
+    gs_, gm_ = torch.autograd.grad(o, (st, mt), torch.from_numpy(go).double())
+    gm, gs = E.mask_bwd(spec, m, go, mode, pre_tanh)
+    assert rel(gm, gm_.numpy()) < 1e-5
+    assert rel(gs, np.nan_to_num(gs_.numpy())) < 1e-5
+
+
+def test_emu_mask_matches_dcunet_and_dccrn_golden():
+    g = golden("dcunet_mask_E")
+    out = E.mask_fwd(np.ascontiguousarray(g["spec"]), np.ascontiguousarray(g["raw_mask"]), 1, True)
+    assert rel(out, g["out"]) < 1e-5
+    for mode, code in (("E", 1), ("C", 2), ("R", 3)):
+        g = golden(f"dccrn_mask_{mode}")
+        nf = g["specs"].shape[1] // 2
+        spec = np.ascontiguousarray(np.stack([g["specs"][:, :nf], g["specs"][:, nf:]], -1))
+        mask = np.ascontiguousarray(np.stack([g["mask_re"], g["mask_im"]], -1))
+        out = E.mask_fwd(spec, mask, code, False)
+        assert rel(np.concatenate([out[..., 0], out[..., 1]], 1), g["out_spec"]) < 1e-5
+
+
+def test_emu_mrstft_loss_and_grad():
+    rng = np.random.default_rng(1)
+    N = 5000
+    ref = rng.standard_normal((2, N)).astype(np.float32)
+    est = (ref + 0.1 * rng.standard_normal((2, N))).astype(np.float32)
+    sums, loss = E.mrstft_fwd(est, ref)
+    l64, g64 = o64.mrstft_loss(est, ref, with_grad=True)
+    assert abs(loss - l64) / l64 < 1e-5
+    parts = np.array(oref.mrstft_partials_ref(torch.from_numpy(est)[:, None], torch.from_numpy(ref)[:, None]))
+    assert rel(sums.reshape(3, 3), parts[:, :3]) < 1e-5
+    g = E.mrstft_bwd(est, ref, sums, 0.5)
+    assert not np.isnan(g).any()
+    assert rel(g, 0.5 * g64) < 1e-3                 # north_star: loss and gradients within 1e-3
+
+
+@pytest.mark.parametrize("name", ["conv_a", "conv_b", "conv_c"])
+def test_emu_conv_stft_matches_reference_golden(name):
+    g = golden(name)
+    wl, inc, nfft, _ = (int(v) for v in g["meta"])
+    s = E.conv_stft_fwd(np.ascontiguousarray(g["x"][:, 0]), wl, inc, nfft)
+    assert s.shape == g["spec"].shape
+    assert rel(s, g["spec"]) < 1e-5

@@ -1,0 +1,223 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the reference's golden
+vectors.  Tolerances are BASELINE.json's: spectra / waveforms 1e-4 relative, loss / gradients
+1e-3 relative (relative = max |err| / max |ref|)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+TOL_SPEC = 1e-4
+TOL_GRAD = 1e-3
+
+
+@pytest.fixture(scope="module")
+def se():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    import speech_enhancement_pytorch_b200 as m
+    m._native.lib()          # fail loudly if the extension is missing
+    return m
+
+
+@pytest.fixture(scope="module")
+def oref():
+    from oracle import spectral_oracle
+    return spectral_oracle
+
+
+def cfg(n, h, w):
+    return types.SimpleNamespace(n_fft=n, hop_length=h, win_length=w, center=True)
+
+
+def rel(a, b):
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+GOLD = ["stft_n512", "stft_n1024", "stft_n2048", "stft_n512_hop256", "stft_n512_win400", "stft_n512_4d",
+        "stft_n512_short_len", "stft_n512_long_len", "stft_n1024_multiple", "stft_structured"]
+
+
+@pytest.mark.parametrize("name", GOLD)
+def test_golden_stft_istft(se, name):
+    g = golden(name)
+    n, h, w, length = (int(v) for v in g["meta"])
+    c = cfg(n, h, w)
+    x = torch.from_numpy(g["x"]).cuda()
+    spec = se.stft_custom(x, c)
+    assert spec.shape == g["spec"].shape and spec.dtype == torch.float32 and spec.is_contiguous()
+    assert rel(spec, torch.from_numpy(g["spec"])) < TOL_SPEC
+    y = se.istft_custom(torch.from_numpy(g["spec"]).cuda(), length, c)
+    assert y.shape == g["y"].shape
+    assert rel(y, torch.from_numpy(g["y"])) < TOL_SPEC
+    if "spec2" in g:
+        y2 = se.istft_custom(torch.from_numpy(g["spec2"]).cuda(), length, c)
+        assert rel(y2, torch.from_numpy(g["y2"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("name", ["grad_n512", "grad_n1024", "grad_n512_win400"])
+def test_golden_autograd(se, name):
+    g = golden(name)
+    n, h, w, N = (int(v) for v in g["meta"])
+    c = cfg(n, h, w)
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    spec = se.stft_custom(x, c)
+    (gx,) = torch.autograd.grad(spec, x, torch.from_numpy(g["gspec"]).cuda())
+    assert rel(gx, torch.from_numpy(g["gx"])) < TOL_SPEC
+    s = torch.from_numpy(g["s"]).cuda().requires_grad_(True)
+    y = se.istft_custom(s, N, c)
+    (gs,) = torch.autograd.grad(y, s, torch.from_numpy(g["gy"]).cuda())
+    assert rel(gs, torch.from_numpy(g["gs"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("n,h,w,shape", [(512, 128, 512, (3, 2, 16000)), (1024, 256, 1024, (4, 1, 16384)),
+                                         (2048, 512, 2048, (2, 1, 44100)), (1024, 512, 1024, (2, 2, 1, 9999)),
+                                         (512, 128, 400, (2, 1, 16001))])
+def test_seeded_vs_oracle(se, oref, n, h, w, shape):
+    g = torch.Generator().manual_seed(n + shape[-1])
+    x = torch.randn(*shape, generator=g)
+    c = cfg(n, h, w)
+    ref_spec = oref.stft_custom_ref(x, c)
+    spec = se.stft_custom(x.cuda(), c)
+    assert rel(spec, ref_spec) < TOL_SPEC
+    pert = ref_spec + 0.01 * torch.randn(ref_spec.shape, generator=g)
+    for length in (shape[-1], shape[-1] - 100):
+        assert rel(se.istft_custom(pert.cuda(), length, c), oref.istft_custom_ref(pert, length, c)) < TOL_SPEC
+
+
+def test_round_trip_property_full_size(se):
+    """The reference's own pin: istft(stft(x)) == x to 1e-5 (test/test_train.py:97-100), at
+    BASELINE config sizes (16x4 s / 64x4 s / 128x4 s)."""
+    for n, h, rows in ((512, 128, 16), (1024, 256, 64), (2048, 512, 128)):
+        x = torch.randn(rows, 1, 64000, device="cuda")
+        c = cfg(n, h, n)
+        y = se.istft_custom(se.stft_custom(x, c), 64000, c)
+        assert float((y - x).abs().max()) < 1e-5
+
+
+def test_linearity_and_adjoint_property_full_size(se):
+    """<stft(x), G> == <x, stft^T(G)> and linearity, at cfg2 size."""
+    c = cfg(1024, 256, 1024)
+    x = torch.randn(64, 1, 64000, device="cuda", requires_grad=True)
+    spec = se.stft_custom(x, c)
+    G = torch.randn_like(spec)
+    (gx,) = torch.autograd.grad(spec, x, G)
+    lhs = float((spec.double() * G.double()).sum())
+    rhs = float((x.double() * gx.double()).sum())
+    assert abs(lhs - rhs) / abs(lhs) < 1e-5
+    x2 = torch.randn_like(x)
+    lin = se.stft_custom(x.detach() + 2 * x2, c) - spec.detach() - 2 * se.stft_custom(x2, c)
+    assert float(lin.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["real", "E", "C", "R"])
+@pytest.mark.parametrize("pre_tanh", [False, True])
+def test_masks_vs_oracle(se, oref, mode, pre_tanh):
+    g = torch.Generator().manual_seed(5)
+    spec = torch.randn(3, 1, 257, 41, 2, generator=g)
+    spec[0, 0, 0, 0] = 0.0
+    mask = torch.randn(*(spec.shape[:-1] if mode == "real" else spec.shape), generator=g)
+    sc = spec.cuda().requires_grad_(True)
+    mc = mask.cuda().requires_grad_(True)
+    out = se.apply_mask(sc, mc, mode, pre_tanh)
+    sr = spec.double().requires_grad_(True)
+    mr = mask.double().requires_grad_(True)
+    ref = oref.mask_apply_ref(sr, mr, mode, pre_tanh)
+    assert rel(out, ref) < TOL_SPEC
+    go = torch.randn(ref.shape, generator=g)
+    go[0, 0, 0, 0] = 0.0
+    gs, gm = torch.autograd.grad(out, (sc, mc), go.cuda())
+    gsr, gmr = torch.autograd.grad(ref, (sr, mr), go.double())
+    assert rel(gm, gmr) < TOL_GRAD
+    assert rel(gs, torch.nan_to_num(gsr)) < TOL_GRAD
+
+
+def test_mask_golden_from_reference_models(se):
+    g = golden("dcunet_mask_E")
+    out = se.apply_mask(torch.from_numpy(g["spec"]).cuda(), torch.from_numpy(g["raw_mask"]).cuda(), "E", True)
+    assert rel(out, torch.from_numpy(g["out"])) < TOL_SPEC
+    for mode in ("E", "C", "R"):
+        g = golden(f"dccrn_mask_{mode}")
+        out = se.apply_mask_dccrn(torch.from_numpy(g["specs"]).cuda(), torch.from_numpy(g["mask_re"]).cuda(),
+                                  torch.from_numpy(g["mask_im"]).cuda(), mode)
+        assert rel(out, torch.from_numpy(g["out_spec"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 6000), (3, 2, 1, 16000)])
+def test_mrstft_loss_and_gradient(se, oref, shape):
+    g = torch.Generator().manual_seed(1236)
+    ref = torch.randn(*shape, generator=g)
+    est = ref + 0.1 * torch.randn(*shape, generator=g)
+    e_ref = est.clone().requires_grad_(True)
+    l_ref = oref.mrstft_loss_ref(e_ref, ref)
+    (g_ref,) = torch.autograd.grad(l_ref, e_ref)
+    e = est.cuda().requires_grad_(True)
+    loss = se.loss_mrstft(e, ref.cuda())
+    assert loss.dim() == 0
+    (grad,) = torch.autograd.grad(2.0 * loss, e)
+    assert abs(float(loss) - float(l_ref)) / float(l_ref) < TOL_GRAD
+    assert rel(grad, 2.0 * g_ref) < 2 * TOL_GRAD      # two fp32 paths, each ~5e-4 from float64 (see test below)
+    from oracle import spectral_np64 as o64
+    l64, g64 = o64.mrstft_loss(est.numpy(), ref.numpy(), with_grad=True)
+    assert abs(float(loss) - l64) / l64 < 1e-5
+    assert rel(grad.reshape(-1, shape[-1]), torch.from_numpy(2.0 * g64)) < TOL_GRAD
+
+
+def test_mrstft_full_size_survey_value(se):
+    """seed 1236, est = ref + 0.1 N(0,1), 128x1x64000 -> loss 0.168027."""
+    g = torch.Generator().manual_seed(1236)
+    ref = torch.randn(128, 1, 64000, generator=g)
+    est = ref + 0.1 * torch.randn(128, 1, 64000, generator=g)
+    loss = se.loss_mrstft(est.cuda(), ref.cuda())
+    assert abs(float(loss) - 0.168027) < 2e-4
+    # determinism of the two-stage reduction
+    assert float(se.loss_mrstft(est.cuda(), ref.cuda())) == float(loss)
+
+
+def test_chain_matches_oracle_end_to_end(se, oref):
+    """stft -> 'E' mask (pre-tanh) -> istft -> MR-STFT loss, gradient wrt the raw mask (cfg2 shape, small batch)."""
+    g = torch.Generator().manual_seed(9)
+    c = cfg(1024, 256, 1024)
+    x = torch.randn(2, 1, 16384, generator=g)
+    clean = x + 0.3 * torch.randn(2, 1, 16384, generator=g)
+    raw = torch.randn(2, 1, 513, 65, 2, generator=g)
+
+    def run(stft, mask, istft, loss, dev):
+        r = raw.to(dev).requires_grad_(True)
+        y = istft(mask(stft(x.to(dev), c), r), 16384, c)
+        l = loss(y, clean.to(dev))
+        return y, l, torch.autograd.grad(l, r)[0]
+
+    y, l, gr = run(se.stft_custom, lambda s, m: se.apply_mask(s, m, "E", True), se.istft_custom, se.loss_mrstft, "cuda")
+    y0, l0, gr0 = run(oref.stft_custom_ref, lambda s, m: oref.mask_apply_ref(s, m, "E", True), oref.istft_custom_ref,
+                      oref.mrstft_loss_ref, "cpu")
+    assert rel(y, y0) < TOL_SPEC
+    assert abs(float(l) - float(l0)) / float(l0) < TOL_GRAD
+    assert rel(gr, gr0) < 2 * TOL_GRAD
+
+
+def test_errors_match_reference_behaviour(se):
+    x = torch.randn(1, 1, 4096, device="cuda")
+    with pytest.raises(NotImplementedError):
+        se.stft_custom(x, cfg(320, 80, 320))
+    with pytest.raises(TypeError):
+        se.stft_custom(x.double(), cfg(512, 128, 512))
+    with pytest.raises((ValueError, RuntimeError)):
+        se.stft_custom(torch.randn(1, 1, 200, device="cuda"), cfg(512, 128, 512))   # reflect pad >= N
+    spec = se.stft_custom(x.bfloat16(), cfg(512, 128, 512))                          # bf16 in -> fp32 spectra
+    assert spec.dtype == torch.float32
+
+
+@pytest.mark.parametrize("name", ["conv_a", "conv_b", "conv_c"])
+def test_conv_stft_golden(se, name):
+    g = golden(name)
+    wl, inc, nfft, length = (int(v) for v in g["meta"])
+    st = se.ConvSTFT(wl, inc, nfft, "hann", "complex")
+    spec = st(torch.from_numpy(g["x"]).cuda())
+    assert spec.shape == g["spec"].shape
+    assert rel(spec, torch.from_numpy(g["spec"])) < TOL_SPEC
