@@ -345,7 +345,7 @@ int se_mrstft_loss_bwd(const float* est, const float* ref, const double* sums, c
     return 0;
 }
 
+}  // extern "C"
+
 // ---------------------------------------------------------------- fused enhance + DCCRN transforms
 #include "se_capi_ext.inc"
-
-}  // extern "C"

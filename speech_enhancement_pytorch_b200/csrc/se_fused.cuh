@@ -1,3 +1,151 @@
-// se_fused.cuh -- fused wave -> STFT -> mask -> iSTFT -> wave kernels (placeholder).
+// se_fused.cuh -- wave -> STFT -> mask -> iSTFT -> wave in ONE kernel (and its backward to the
+// raw mask).  The spectrum never touches HBM: 2S + M bytes per row instead of 2S + 4P + M
+// (SURVEY.md 8d), where P ~ 4S.  Same numerics as stft_custom -> model tail -> istft_custom:
+// the analysis window carries the reference's 1/win_length (the polar mask is not scale
+// invariant because of its 1e-8), the synthesis window carries win_length / n.
 #pragma once
 #include "se_kernels.cuh"
+
+namespace se {
+
+struct EnhArgs {
+    Tables ta;               // analysis tables: window * 0.5 / win_length
+    Tables ts;               // synthesis tables: window * win_length / n   (env tables valid here)
+    const float* x;          // [rows, N]
+    const float* mask;       // [rows, F, T] (REAL) or [rows, F, T, 2]
+    const float* gy;         // bwd: [rows, N]
+    float* out;              // fwd: y [rows, N]; bwd: gmask
+    int nsample, nframe;
+    int b_lo, b_hi, nchunks; // fwd (synthesis-style chunking)
+    int gpc;                 // bwd (analysis-style chunking)
+    int mode, pre_tanh;
+};
+
+template <class G>
+__device__ __forceinline__ float2 load_mask(const EnhArgs& a, size_t row, int k, int t) {
+    const size_t idx = (row * G::F + k) * (size_t)a.nframe + t;
+    if (a.mode == 0) {
+        float m = __ldg(a.mask + idx);
+        if (a.pre_tanh) m = tanhf(m);
+        return make_float2(m, 0.f);
+    }
+    float2 m = __ldg(reinterpret_cast<const float2*>(a.mask) + idx);
+    if (a.pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
+    return m;
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
+    AnaArgs la;
+    la.tb = a.ta; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;
+    SynArgs sa;
+    sa.tb = a.ts; sa.nsample = G::N + G::HOP * (a.nframe - 1); sa.out_len = a.nsample; sa.nframe = a.nframe;
+    float* out_row = a.out + (size_t)row * a.nsample;
+    float2 carry[G::TA][G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i)
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
+    for (int g = 0; g < c.ngroups; ++g) {
+        const int f_base = c.f0 + g * G::FR;
+        const int t = f_base + fr;
+        const bool live = (t >= 0 && t < a.nframe);
+        fill_stage<G, LOAD_REFLECT>(iobuf, a.x + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+        __syncthreads();
+        analysis_passes<G>(iobuf, a.ta, zb, unit, fr);
+#pragma unroll
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.ta, p, fr, xa, xb, nyq);
+            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+            for (int k = 0; k < 17; ++k) {
+                if (k == 16 && p != 0) { nyq = make_float2(0.f, 0.f); continue; }
+                const int bin = k < 8 ? qa + G::S * k : (k < 16 ? qb + G::S * (k - 8) : G::M);
+                float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                if (live) {
+                    const float2 m = load_mask<G>(a, row, bin, t);
+                    v = a.mode == 0 ? make_float2(v.x * m.x, v.y * m.x) : MaskMath::fwd(a.mode, v, m);
+                } else {
+                    v = make_float2(0.f, 0.f);
+                }
+                if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
+            }
+            synthesis_task<G>(zb, a.ts, p, fr, xa, xb, nyq);
+        }
+        synthesis_tail<G>(zb, a.ts, iobuf, unit, fr, carry);
+        emit_istft<G>(iobuf, out_row, f_base, c, sa, tid);
+        __syncthreads();
+    }
+}
+
+// backward to the raw mask: X = STFT(x) recomputed, gY = iSTFT^T(gy), then the mask adjoint.
+// Two working buffers (x and gy transforms are both needed per bin) -> n_fft <= 1024 only.
+template <class G>
+__global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
+    SE_SMEM_DECL;
+    float2* zbx = reinterpret_cast<float2*>(se_smem);
+    float2* zbg = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB);
+    float* stage = reinterpret_cast<float*>(se_smem + 2 * Smem<G>::ZB);
+    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    AnaArgs lx;
+    lx.tb = a.ta; lx.nsample = a.nsample; lx.nframe = a.nframe; lx.in_len = a.nsample; lx.pad = 0;
+    AnaArgs lg;
+    lg.tb = a.ts; lg.nsample = G::N + G::HOP * (a.nframe - 1); lg.nframe = a.nframe; lg.in_len = a.nsample; lg.pad = 0;
+    for (int g = 0; g < a.gpc; ++g) {
+        const int f_base = (chunk * a.gpc + g) * G::FR;
+        if (f_base >= a.nframe) break;
+        const int t = f_base + fr;
+        fill_stage<G, LOAD_REFLECT>(stage, a.x + (size_t)row * a.nsample, f_base * G::HOP, lx, tid);
+        __syncthreads();
+        analysis_passes<G>(stage, a.ta, zbx, unit, fr);          // ends with a barrier: stage is free
+        fill_stage<G, LOAD_ENV>(stage, a.gy + (size_t)row * a.nsample, f_base * G::HOP, lg, tid);
+        __syncthreads();
+        analysis_passes<G>(stage, a.ts, zbg, unit, fr);
+        if (t < a.nframe) {
+#pragma unroll
+            for (int i = 0; i < G::TC; ++i) {
+                const int p = unit + i * G::NU;
+                float2 xa[8], xb[8], xn, ga[8], gb[8], gn;
+                analysis_task<G>(zbx, a.ta, p, fr, xa, xb, xn);
+                analysis_task<G>(zbg, a.ts, p, fr, ga, gb, gn);
+                const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+                for (int k = 0; k < 17; ++k) {
+                    if (k == 16 && p != 0) continue;
+                    const int bin = k < 8 ? qa + G::S * k : (k < 16 ? qb + G::S * (k - 8) : G::M);
+                    const float2 x = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : xn);
+                    float2 gy = k < 8 ? ga[k] : (k < 16 ? gb[k - 8] : gn);
+                    // iSTFT adjoint: c_k / n with the 2/n folded into the window -> edges get 1/2, real only
+                    if (p == 0 && (k == 0 || k == 16)) gy = make_float2(0.5f * gy.x, 0.f);
+                    const size_t idx = ((size_t)row * G::F + bin) * (size_t)a.nframe + t;
+                    if (a.mode == 0) {
+                        float m = __ldg(a.mask + idx);
+                        if (a.pre_tanh) m = tanhf(m);
+                        float gm = x.x * gy.x + x.y * gy.y;
+                        if (a.pre_tanh) gm *= (1.f - m * m);
+                        a.out[idx] = gm;
+                    } else {
+                        float2 m = __ldg(reinterpret_cast<const float2*>(a.mask) + idx);
+                        if (a.pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
+                        float2 gm, gx;
+                        MaskMath::bwd(a.mode, x, m, gy, gm, gx);
+                        if (a.pre_tanh) gm = make_float2(gm.x * (1.f - m.x * m.x), gm.y * (1.f - m.y * m.y));
+                        reinterpret_cast<float2*>(a.out)[idx] = gm;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace se

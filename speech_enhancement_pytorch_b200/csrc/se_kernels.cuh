@@ -285,7 +285,7 @@ template <class G> struct Smem {
 // ================================================================== kernels
 // wave-like rows -> spectrum.  LMODE picks the padded-signal definition, PLANAR the layout.
 template <class G, int LMODE, bool PLANAR>
-__global__ void __launch_bounds__(G::NT) k_analysis(const AnaArgs a) {
+__global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(G::NT) k_analysis(const AnaArgs a) {
 
 // spectrum -> wave-like rows.  EMODE: ISTFT (envelope + trim) or ADJ (reflect fold-back).
 template <class G, int EMODE>
-__global__ void __launch_bounds__(G::NT) k_synthesis(const SynArgs a) {
+__global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
@@ -368,7 +368,7 @@ struct LossArgs {
 #define SE_MRSTFT_CLAMP 1e-7f
 
 template <class G>
-__global__ void __launch_bounds__(G::NT) k_loss_fwd(const LossArgs a) {
+__global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
@@ -383,45 +383,33 @@ __global__ void __launch_bounds__(G::NT) k_loss_fwd(const LossArgs a) {
         if (f_base >= a.nframe) break;
         const int t = f_base + fr;
         float pb[G::TC][17];
-        fill_stage<G, LOAD_REFLECT>(stage, a.ref + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
-        __syncthreads();
-        analysis_passes<G>(stage, a.tb, zb, unit, fr);
+#pragma unroll 1
+        for (int sig = 0; sig < 2; ++sig) {              // 0: reference magnitudes, 1: estimate + statistics
+            fill_stage<G, LOAD_REFLECT>(stage, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+            __syncthreads();
+            analysis_passes<G>(stage, a.tb, zb, unit, fr);
 #pragma unroll
-        for (int i = 0; i < G::TC; ++i) {
-            const int p = unit + i * G::NU;
-            float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
-#pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-                pb[i][k4] = xa[k4].x * xa[k4].x + xa[k4].y * xa[k4].y;
-                pb[i][8 + k4] = xb[k4].x * xb[k4].x + xb[k4].y * xb[k4].y;
-            }
-            pb[i][16] = nyq.x * nyq.x;
-        }
-        fill_stage<G, LOAD_REFLECT>(stage, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
-        __syncthreads();
-        analysis_passes<G>(stage, a.tb, zb, unit, fr);
-#pragma unroll
-        for (int i = 0; i < G::TC; ++i) {
-            const int p = unit + i * G::NU;
-            float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
-            if (t < a.nframe) {
+            for (int i = 0; i < G::TC; ++i) {
+                const int p = unit + i * G::NU;
+                float2 xa[8], xb[8], nyq;
+                analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
 #pragma unroll
                 for (int k = 0; k < 17; ++k) {
-                    if (k == 16 && p != 0) continue;
                     const float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
-                    const float ca = fmaxf(v.x * v.x + v.y * v.y, SE_MRSTFT_CLAMP);
-                    const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
-                    const float ma = sqrtf(ca), mb = sqrtf(cb);
-                    const float d = mb - ma;
-                    s_d2 += d * d;
-                    s_b2 += cb;
-                    s_lm += 0.5f * fabsf(logf(cb) - logf(ca));
+                    const float pw = v.x * v.x + v.y * v.y;
+                    if (sig == 0) {
+                        pb[i][k] = pw;
+                    } else if (t < a.nframe && !(k == 16 && p != 0)) {
+                        const float ca = fmaxf(pw, SE_MRSTFT_CLAMP);
+                        const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
+                        const float d = sqrtf(cb) - sqrtf(ca);
+                        s_d2 += d * d;
+                        s_b2 += cb;
+                        s_lm += 0.5f * fabsf(logf(cb) - logf(ca));
+                    }
                 }
             }
         }
-        __syncthreads();
     }
     // block reduction -> one deterministic partial per CTA
 #pragma unroll
@@ -440,7 +428,7 @@ __global__ void __launch_bounds__(G::NT) k_loss_fwd(const LossArgs a) {
 }
 
 template <class G>
-__global__ void __launch_bounds__(G::NT) k_loss_bwd(const LossArgs a) {
+__global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);          // stage, later ostage
@@ -466,45 +454,42 @@ __global__ void __launch_bounds__(G::NT) k_loss_bwd(const LossArgs a) {
         const int t = f_base + fr;
         const bool live = (t >= 0 && t < a.nframe);
         float pb[G::TC][17];
-        fill_stage<G, LOAD_REFLECT>(iobuf, a.ref + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
-        __syncthreads();
-        analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
+#pragma unroll 1
+        for (int sig = 0; sig < 2; ++sig) {              // 0: reference magnitudes, 1: estimate -> gradient spectrum
+            fill_stage<G, LOAD_REFLECT>(iobuf, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+            __syncthreads();
+            analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
 #pragma unroll
-        for (int i = 0; i < G::TC; ++i) {
-            const int p = unit + i * G::NU;
-            float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            for (int i = 0; i < G::TC; ++i) {
+                const int p = unit + i * G::NU;
+                float2 xa[8], xb[8], nyq;
+                analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+                if (sig == 0) {
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) {
-                pb[i][k4] = xa[k4].x * xa[k4].x + xa[k4].y * xa[k4].y;
-                pb[i][8 + k4] = xb[k4].x * xb[k4].x + xb[k4].y * xb[k4].y;
-            }
-            pb[i][16] = nyq.x * nyq.x;
-        }
-        fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
-        __syncthreads();
-        analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
+                    for (int k = 0; k < 17; ++k) {
+                        const float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                        pb[i][k] = v.x * v.x + v.y * v.y;
+                    }
+                } else {
 #pragma unroll
-        for (int i = 0; i < G::TC; ++i) {
-            const int p = unit + i * G::NU;
-            float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
-#pragma unroll
-            for (int k = 0; k < 17; ++k) {
-                float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
-                const float pa = v.x * v.x + v.y * v.y;
-                float coef = 0.f;
-                if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
-                    const float ma = sqrtf(pa), mb = sqrtf(fmaxf(pb[i][k], SE_MRSTFT_CLAMP));
-                    const float sg = ma > mb ? 1.f : (ma < mb ? -1.f : 0.f);
-                    coef = (alpha * (ma - mb) + beta * sg / ma) / ma;
+                    for (int k = 0; k < 17; ++k) {
+                        float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                        const float pa = v.x * v.x + v.y * v.y;
+                        float coef = 0.f;
+                        if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
+                            const float ma = sqrtf(pa), mb = sqrtf(fmaxf(pb[i][k], SE_MRSTFT_CLAMP));
+                            const float sg = ma > mb ? 1.f : (ma < mb ? -1.f : 0.f);
+                            coef = (alpha * (ma - mb) + beta * sg / ma) / ma;
+                        }
+                        // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
+                        if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
+                        v = make_float2(v.x * coef, v.y * coef);
+                        if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
+                    }
+                    synthesis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
                 }
-                // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
-                if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
-                v = make_float2(v.x * coef, v.y * coef);
-                if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
             }
-            synthesis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            if (sig == 0) __syncthreads();               // pass C reads of zb done before the next pass A writes
         }
         synthesis_tail<G>(zb, a.tb, iobuf, unit, fr, carry);
         emit_adj<G>(iobuf, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);

@@ -206,6 +206,14 @@ class _Enhance(torch.autograd.Function):
         rows, n = x.shape
         gy = gy.contiguous()
         gmask = torch.empty_like(mask)
+        if n_fft > 1024:
+            # two 2048-point working sets do not fit one SM's shared memory: compose our own kernels
+            spec = stft_rows(x, n_fft, hop, win_length, 1.0 / win_length)
+            gspec = istft_rows_adjoint(gy, spec.shape[2], n_fft, hop, win_length, float(win_length))
+            with nv.on_device(x.device):
+                nv.check(nv.lib().se_mask_bwd(spec.data_ptr(), mask.data_ptr(), gspec.data_ptr(), gmask.data_ptr(), 0,
+                                              spec.numel() // 2, mode, int(pre_tanh), nv.stream_ptr(x.device)))
+            return None, gmask, None, None, None, None, None
         with nv.on_device(x.device):
             nv.check(nv.lib().se_enhance_bwd(gy.data_ptr(), x.data_ptr(), mask.data_ptr(), gmask.data_ptr(), rows, n,
                                              n_fft, hop, win_length, mode, int(pre_tanh), nv.stream_ptr(x.device)))

@@ -139,3 +139,43 @@ def test_emu_conv_stft_matches_reference_golden(name):
     s = E.conv_stft_fwd(np.ascontiguousarray(g["x"][:, 0]), wl, inc, nfft)
     assert s.shape == g["spec"].shape
     assert rel(s, g["spec"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["conv_a", "conv_b", "conv_c"])
+def test_emu_conv_istft_matches_reference_golden_and_autograd(name):
+    g = golden(name)
+    wl, inc, nfft, length = (int(v) for v in g["meta"])
+    for ks, ky in (("spec", "y"), ("spec2", "y2")):
+        y = E.conv_istft_fwd(np.ascontiguousarray(g[ks]), g[ky].shape[-1], wl, inc, nfft)
+        assert not np.isnan(y).any()
+        assert rel(y, g[ky][:, 0]) < 1e-5
+    st = torch.from_numpy(g["spec2"]).double().requires_grad_(True)
+    yr = oref.conv_istft_ref(st, wl, inc, nfft, "hann", None if length < 0 else length)
+    gy = np.random.default_rng(0).standard_normal(yr.shape).astype(np.float32)
+    (gs,) = torch.autograd.grad(yr, st, torch.from_numpy(gy).double())
+    got = E.conv_istft_bwd(np.ascontiguousarray(gy[:, 0]), st.shape[-1], wl, inc, nfft)
+    assert rel(got, gs.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("n,hop,win,N", [(512, 128, 512, 2085), (1024, 256, 1024, 4351), (512, 256, 512, 3000),
+                                         (512, 128, 400, 2500), (2048, 512, 2048, 8705)])
+@pytest.mark.parametrize("mode,name", [(0, "real"), (1, "E"), (2, "C")])
+def test_emu_fused_enhance(n, hop, win, N, mode, name):
+    import types
+    rng = np.random.default_rng(n + mode)
+    pre_tanh = mode == 1
+    F, T = n // 2 + 1, 1 + N // hop
+    cfg = types.SimpleNamespace(n_fft=n, hop_length=hop, win_length=win, center=True)
+    x = rng.standard_normal((2, N)).astype(np.float32)
+    m = rng.standard_normal((2, F, T) if mode == 0 else (2, F, T, 2)).astype(np.float32)
+    y = E.enhance_fwd(x, m, n, hop, win, mode, pre_tanh)
+    xt = torch.from_numpy(x)[:, None].double()
+    mt = torch.from_numpy(m)[:, None].double().requires_grad_(True)
+    yr = oref.istft_custom_ref(oref.mask_apply_ref(oref.stft_custom_ref(xt, cfg), mt, name, pre_tanh), N, cfg)
+    assert not np.isnan(y).any()
+    assert rel(y, yr.detach().numpy()[:, 0]) < 2e-6
+    if n <= 1024:
+        gy = rng.standard_normal((2, N)).astype(np.float32)
+        (gm_ref,) = torch.autograd.grad(yr, mt, torch.from_numpy(gy)[:, None].double())
+        gm = E.enhance_bwd(gy, x, m, n, hop, win, mode, pre_tanh)
+        assert rel(gm, gm_ref.numpy()[:, 0]) < 2e-6

@@ -161,11 +161,20 @@ def test_mrstft_loss_and_gradient(se, oref, shape):
     assert loss.dim() == 0
     (grad,) = torch.autograd.grad(2.0 * loss, e)
     assert abs(float(loss) - float(l_ref)) / float(l_ref) < TOL_GRAD
-    assert rel(grad, 2.0 * g_ref) < 2 * TOL_GRAD      # two fp32 paths, each ~5e-4 from float64 (see test below)
+    # Ground truth is the float64 restatement: the CUDA path must sit within 1e-3 of it.  The
+    # reference's own fp32 torch path is itself ~5e-4..1e-3 away from float64 on this loss
+    # (1/|A|^2 amplifies fp32 FFT noise in near-silent bins), so the fp32-vs-fp32 distance is
+    # bounded by the triangle inequality rather than by 1e-3 directly.
     from oracle import spectral_np64 as o64
     l64, g64 = o64.mrstft_loss(est.numpy(), ref.numpy(), with_grad=True)
+    g64 = torch.from_numpy(2.0 * g64).reshape(shape)
     assert abs(float(loss) - l64) / l64 < 1e-5
-    assert rel(grad.reshape(-1, shape[-1]), torch.from_numpy(2.0 * g64)) < TOL_GRAD
+    err_ours = rel(grad, g64)
+    err_ref32 = rel(2.0 * g_ref, g64)
+    assert err_ours < TOL_GRAD, (err_ours, err_ref32)
+    assert rel(grad, 2.0 * g_ref) < err_ref32 + TOL_GRAD
+    l2 = float((grad.cpu().double() - 2.0 * g_ref.double()).norm() / (2.0 * g_ref.double()).norm())
+    assert l2 < TOL_GRAD
 
 
 def test_mrstft_full_size_survey_value(se):
@@ -198,7 +207,8 @@ def test_chain_matches_oracle_end_to_end(se, oref):
                       oref.mrstft_loss_ref, "cpu")
     assert rel(y, y0) < TOL_SPEC
     assert abs(float(l) - float(l0)) / float(l0) < TOL_GRAD
-    assert rel(gr, gr0) < 2 * TOL_GRAD
+    l2 = float((gr.cpu().double() - gr0.double()).norm() / gr0.double().norm())
+    assert l2 < TOL_GRAD and rel(gr, gr0) < 3 * TOL_GRAD
 
 
 def test_errors_match_reference_behaviour(se):
@@ -221,3 +231,82 @@ def test_conv_stft_golden(se, name):
     spec = st(torch.from_numpy(g["x"]).cuda())
     assert spec.shape == g["spec"].shape
     assert rel(spec, torch.from_numpy(g["spec"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("name", ["conv_a", "conv_b", "conv_c"])
+def test_conv_istft_golden_and_autograd(se, oref, name):
+    g = golden(name)
+    wl, inc, nfft, length = (int(v) for v in g["meta"])
+    length = None if length < 0 else length
+    ist = se.ConviSTFT(wl, inc, nfft, length, "hann", "complex")
+    for ks, ky in (("spec", "y"), ("spec2", "y2")):
+        y = ist(torch.from_numpy(g[ks]).cuda())
+        assert y.shape == g[ky].shape
+        assert rel(y, torch.from_numpy(g[ky])) < TOL_SPEC
+    s = torch.from_numpy(g["spec2"]).cuda().requires_grad_(True)
+    y = ist(s)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
+    (gs,) = torch.autograd.grad(y, s, gy.cuda())
+    sr = torch.from_numpy(g["spec2"]).double().requires_grad_(True)
+    (gsr,) = torch.autograd.grad(oref.conv_istft_ref(sr, wl, inc, nfft, "hann", length), sr, gy.double())
+    assert rel(gs, gsr) < TOL_SPEC
+
+
+def test_conv_polar_golden(se):
+    g = golden("conv_polar")
+    st = se.ConvSTFT(400, 100, 512, "hann", "real")
+    mags, phase = st(torch.from_numpy(g["x"]).cuda())
+    assert rel(mags, torch.from_numpy(g["mags"])) < TOL_SPEC
+    ist = se.ConviSTFT(400, 100, 512, None, "hann", "real")
+    y = ist(torch.from_numpy(g["mags"]).cuda(), torch.from_numpy(g["phase"]).cuda())
+    assert rel(y, torch.from_numpy(g["y"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("mode", ["E", "C", "R"])
+def test_dccrn_wave_to_wave_golden(se, mode):
+    """Real DCCRN forward captured by hooks: specs = stft(x); wav = clamp(istft(mask(specs)))."""
+    g = golden(f"dccrn_mask_{mode}")
+    st = se.ConvSTFT(400, 100, 512, "hann", "complex")
+    ist = se.ConviSTFT(400, 100, 512, 1600, "hann", "complex")
+    specs = st(torch.from_numpy(g["x"]).cuda())
+    assert rel(specs, torch.from_numpy(g["specs"])) < TOL_SPEC
+    out_spec = se.apply_mask_dccrn(specs, torch.from_numpy(g["mask_re"]).cuda(), torch.from_numpy(g["mask_im"]).cuda(), mode)
+    wav = torch.clamp_(ist(out_spec), -1, 1)          # dccrn.py:228 clamps the module output in place
+    assert wav.shape == g["wav"].shape
+    assert rel(wav, torch.from_numpy(g["wav"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("n,h,w,N", [(512, 128, 512, 16000), (1024, 256, 1024, 16384), (2048, 512, 2048, 44100),
+                                     (512, 128, 400, 9999)])
+@pytest.mark.parametrize("mode", ["real", "E", "C", "R"])
+def test_fused_enhance_matches_unfused_and_oracle(se, oref, n, h, w, N, mode):
+    g = torch.Generator().manual_seed(n + N)
+    c = cfg(n, h, w)
+    pre_tanh = mode == "E"
+    x = torch.randn(3, 1, N, generator=g)
+    F, T = n // 2 + 1, 1 + N // h
+    mask = torch.randn(*((3, 1, F, T) if mode == "real" else (3, 1, F, T, 2)), generator=g)
+    mr = mask.clone().requires_grad_(True)
+    ref = oref.istft_custom_ref(oref.mask_apply_ref(oref.stft_custom_ref(x, c), mr, mode, pre_tanh), N, c)
+    mc = mask.cuda().requires_grad_(True)
+    y = se.enhance(x.cuda(), mc, c, mode, pre_tanh)
+    assert rel(y, ref) < TOL_SPEC
+    gy = torch.randn(ref.shape, generator=g)
+    (gref,) = torch.autograd.grad(ref, mr, gy)
+    (gm,) = torch.autograd.grad(y, mc, gy.cuda())
+    assert rel(gm, gref) < TOL_GRAD
+    m2 = mask.cuda().requires_grad_(True)
+    y2 = se.istft_custom(se.apply_mask(se.stft_custom(x.cuda(), c), m2, mode, pre_tanh), N, c)
+    assert rel(y, y2) < 1e-5
+    (gm2,) = torch.autograd.grad(y2, m2, gy.cuda())
+    assert rel(gm2, gref) < TOL_GRAD
+
+
+def test_fused_chain_full_size_cfg2(se):
+    """cfg2 at full size: fused and unfused paths agree (size-independent consistency)."""
+    c = cfg(1024, 256, 1024)
+    x = torch.randn(64, 1, 64000, device="cuda")
+    raw = torch.randn(64, 1, 513, 251, 2, device="cuda")
+    y1 = se.enhance(x, raw, c, "E", True)
+    y2 = se.istft_custom(se.apply_mask(se.stft_custom(x, c), raw, "E", True), 64000, c)
+    assert float((y1 - y2).abs().max()) < 1e-5 * float(y2.abs().max())
