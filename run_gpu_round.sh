@@ -10,3 +10,4 @@ echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps
 echo "== ncu launches" ; timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 36 -c 24 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-breakdown > gpurun_out/ncu_launch.log 2>&1 ; echo "ncu1 rc=$?" ; tail -3 gpurun_out/ncu_launch.log
 echo "== ncu full" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(loss|analysis|synthesis|enhance|mask)' -s 24 -c 8 -o gpurun_out/prof -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-breakdown > gpurun_out/ncu_full.log 2>&1 ; echo "ncu2 rc=$?" ; tail -3 gpurun_out/ncu_full.log
 ls -la gpurun_out
+echo "== ncu full (unfused drop-in ops)" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_(analysis|synthesis|mask)' -s 15 -c 5 -o gpurun_out/prof_unfused -f python bench.py --fused 0 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-breakdown > gpurun_out/ncu_full2.log 2>&1 ; echo "ncu3 rc=$?" ; tail -2 gpurun_out/ncu_full2.log

@@ -1,0 +1,57 @@
+"""N>1 host logic on CPU: world_size-2 gloo.  Each rank takes its utterance shard, forms the 9
+partial sums (with the oracle standing in for the kernels -- there is no GPU here), all-reduces
+them, and must reproduce the single-process batch-global loss."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from speech_enhancement_pytorch_b200 import distributed as sed
+
+
+def test_shard_rows_partitions_exactly():
+    for n in (1, 7, 64, 129):
+        for world in (1, 2, 3, 8):
+            parts = [sed.shard_rows(n, world, r) for r in range(world)]
+            covered = [i for p in parts for i in range(p.start, p.stop)]
+            assert covered == list(range(n))
+            sizes = [p.stop - p.start for p in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sed.shard_rows(4, 2, 2)
+
+
+def _worker(rank, world, port, nsample, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import spectral_oracle as oref
+    g = torch.Generator().manual_seed(4)
+    ref = torch.randn(6, 1, nsample, generator=g)
+    est = ref + 0.2 * torch.randn(6, 1, nsample, generator=g)
+    sl = sed.shard_rows(6, world, rank)
+    parts = oref.mrstft_partials_ref(est[sl], ref[sl])
+    sums = torch.tensor([v for p in parts for v in p[:3]], dtype=torch.float64)
+    sed.all_reduce_sums(sums)
+    out[rank] = sed.loss_from_sums(sums, 6, nsample)
+    dist.destroy_process_group()
+
+
+def test_two_rank_loss_equals_global_loss():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    nsample = 5000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, nsample, out), nprocs=2, join=True)
+    from oracle import spectral_oracle as oref
+    g = torch.Generator().manual_seed(4)
+    ref = torch.randn(6, 1, nsample, generator=g)
+    est = ref + 0.2 * torch.randn(6, 1, nsample, generator=g)
+    want = float(oref.mrstft_loss_ref(est, ref))
+    assert abs(out[0] - out[1]) < 1e-12
+    assert abs(out[0] - want) / want < 1e-5
