@@ -147,6 +147,20 @@ static int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int w
     return 0;
 }
 
+// MODE (0..3) x TANH -> compile-time template arguments
+#define SE_DISPATCH_MASK(mode, pre_tanh, CALL)                                         \
+    do {                                                                               \
+        if (pre_tanh) {                                                                \
+            constexpr bool TANH = true;                                                \
+            if (mode == 0) { constexpr int MODE = 0; CALL; } else if (mode == 1) { constexpr int MODE = 1; CALL; } \
+            else if (mode == 2) { constexpr int MODE = 2; CALL; } else { constexpr int MODE = 3; CALL; }           \
+        } else {                                                                       \
+            constexpr bool TANH = false;                                               \
+            if (mode == 0) { constexpr int MODE = 0; CALL; } else if (mode == 1) { constexpr int MODE = 1; CALL; } \
+            else if (mode == 2) { constexpr int MODE = 2; CALL; } else { constexpr int MODE = 3; CALL; }           \
+        }                                                                              \
+    } while (0)
+
 #define SE_DISPATCH_GEO(n_fft, hop, CALL)                                              \
     do {                                                                               \
         if (n_fft == 512 && hop == 128) { using G = Geo<512, 128, 256>; CALL; }        \
@@ -258,8 +272,9 @@ int se_mask_fwd(const float* spec, const float* mask, float* out, int64_t count,
     if (mode < 0 || mode > 3) return fail(SE_ERR_UNSUPPORTED, "mask mode must be REAL/E/C/R");
     int64_t blocks = (count + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    cudaError_t e = launch(k_mask_fwd, (unsigned)blocks, 256, 0, (cudaStream_t)stream,
-                           reinterpret_cast<const float2*>(spec), mask, reinterpret_cast<float2*>(out), count, mode, pre_tanh);
+    cudaError_t e;
+    SE_DISPATCH_MASK(mode, pre_tanh, (e = launch(k_mask_fwd_t<MODE, TANH>, (unsigned)blocks, 256, 0, (cudaStream_t)stream,
+                                                 reinterpret_cast<const float2*>(spec), mask, reinterpret_cast<float2*>(out), count)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mask_fwd launch");
 }
 
@@ -269,9 +284,11 @@ int se_mask_bwd(const float* spec, const float* mask, const float* gout, float* 
     if (mode < 0 || mode > 3) return fail(SE_ERR_UNSUPPORTED, "mask mode must be REAL/E/C/R");
     int64_t blocks = (count + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    cudaError_t e = launch(k_mask_bwd, (unsigned)blocks, 256, 0, (cudaStream_t)stream,
-                           reinterpret_cast<const float2*>(spec), mask, reinterpret_cast<const float2*>(gout), gmask,
-                           reinterpret_cast<float2*>(gspec), count, mode, pre_tanh);
+    cudaError_t e;
+    SE_DISPATCH_MASK(mode, pre_tanh, (e = launch(k_mask_bwd_t<MODE, TANH>, (unsigned)blocks, 256, 0, (cudaStream_t)stream,
+                                                 reinterpret_cast<const float2*>(spec), mask,
+                                                 reinterpret_cast<const float2*>(gout), gmask,
+                                                 reinterpret_cast<float2*>(gspec), count)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mask_bwd launch");
 }
 

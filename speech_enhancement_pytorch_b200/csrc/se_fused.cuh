@@ -21,20 +21,14 @@ struct EnhArgs {
     int mode, pre_tanh;
 };
 
-template <class G>
+template <class G, int MODE>
 __device__ __forceinline__ float2 load_mask(const EnhArgs& a, size_t row, int k, int t) {
     const size_t idx = (row * G::F + k) * (size_t)a.nframe + t;
-    if (a.mode == 0) {
-        float m = __ldg(a.mask + idx);
-        if (a.pre_tanh) m = tanhf(m);
-        return make_float2(m, 0.f);
-    }
-    float2 m = __ldg(reinterpret_cast<const float2*>(a.mask) + idx);
-    if (a.pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
-    return m;
+    if (MODE == 0) return make_float2(__ldg(a.mask + idx), 0.f);
+    return __ldg(reinterpret_cast<const float2*>(a.mask) + idx);
 }
 
-template <class G>
+template <class G, int MODE, bool TANH>
 __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
@@ -56,28 +50,34 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
         const int f_base = c.f0 + g * G::FR;
         const int t = f_base + fr;
         const bool live = (t >= 0 && t < a.nframe);
+        const int tc = live ? t : 0;                       // clamped: loads stay in bounds, result zeroed
         fill_stage<G, LOAD_REFLECT>(iobuf, a.x + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
         __syncthreads();
         analysis_passes<G>(iobuf, a.ta, zb, unit, fr);
 #pragma unroll
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
+            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+            // mask values first: 17 independent loads in flight while pass C runs
+            float2 ma[8], mb[8], mn;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                ma[k] = load_mask<G, MODE>(a, row, qa + G::S * k, tc);
+                mb[k] = load_mask<G, MODE>(a, row, qb + G::S * k, tc);
+            }
+            mn = load_mask<G, MODE>(a, row, G::M, tc);
             float2 xa[8], xb[8], nyq;
             analysis_task<G>(zb, a.ta, p, fr, xa, xb, nyq);
-            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+            const float keep = live ? 1.f : 0.f;
 #pragma unroll
-            for (int k = 0; k < 17; ++k) {
-                if (k == 16 && p != 0) { nyq = make_float2(0.f, 0.f); continue; }
-                const int bin = k < 8 ? qa + G::S * k : (k < 16 ? qb + G::S * (k - 8) : G::M);
-                float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
-                if (live) {
-                    const float2 m = load_mask<G>(a, row, bin, t);
-                    v = a.mode == 0 ? make_float2(v.x * m.x, v.y * m.x) : MaskMath::fwd(a.mode, v, m);
-                } else {
-                    v = make_float2(0.f, 0.f);
-                }
-                if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
+            for (int k = 0; k < 8; ++k) {
+                xa[k] = MaskMath::apply<MODE, TANH>(xa[k], ma[k]);
+                xb[k] = MaskMath::apply<MODE, TANH>(xb[k], mb[k]);
+                xa[k] = make_float2(xa[k].x * keep, xa[k].y * keep);
+                xb[k] = make_float2(xb[k].x * keep, xb[k].y * keep);
             }
+            nyq = MaskMath::apply<MODE, TANH>(nyq, mn);
+            nyq = (p == 0) ? make_float2(nyq.x * keep, nyq.y * keep) : make_float2(0.f, 0.f);
             synthesis_task<G>(zb, a.ts, p, fr, xa, xb, nyq);
         }
         synthesis_tail<G>(zb, a.ts, iobuf, unit, fr, carry);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
 
 // backward to the raw mask: X = STFT(x) recomputed, gY = iSTFT^T(gy), then the mask adjoint.
 // Two working buffers (x and gy transforms are both needed per bin) -> n_fft <= 1024 only.
-template <class G>
+template <class G, int MODE, bool TANH>
 __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
     SE_SMEM_DECL;
     float2* zbx = reinterpret_cast<float2*>(se_smem);
@@ -104,43 +104,42 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
         const int f_base = (chunk * a.gpc + g) * G::FR;
         if (f_base >= a.nframe) break;
         const int t = f_base + fr;
+        const bool live = t < a.nframe;
+        const int tc = live ? t : 0;
         fill_stage<G, LOAD_REFLECT>(stage, a.x + (size_t)row * a.nsample, f_base * G::HOP, lx, tid);
         __syncthreads();
         analysis_passes<G>(stage, a.ta, zbx, unit, fr);          // ends with a barrier: stage is free
         fill_stage<G, LOAD_ENV>(stage, a.gy + (size_t)row * a.nsample, f_base * G::HOP, lg, tid);
         __syncthreads();
         analysis_passes<G>(stage, a.ts, zbg, unit, fr);
-        if (t < a.nframe) {
 #pragma unroll
-            for (int i = 0; i < G::TC; ++i) {
-                const int p = unit + i * G::NU;
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {               // unit a, then unit b: 8 bins each (+ Nyquist)
+                const int q = half ? qb : qa;
+                float2 m[8], mn = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m[k] = load_mask<G, MODE>(a, row, q + G::S * k, tc);
+                if (half == 0) mn = load_mask<G, MODE>(a, row, G::M, tc);
                 float2 xa[8], xb[8], xn, ga[8], gb[8], gn;
                 analysis_task<G>(zbx, a.ta, p, fr, xa, xb, xn);
                 analysis_task<G>(zbg, a.ts, p, fr, ga, gb, gn);
-                const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+                if (!live) continue;
 #pragma unroll
-                for (int k = 0; k < 17; ++k) {
-                    if (k == 16 && p != 0) continue;
-                    const int bin = k < 8 ? qa + G::S * k : (k < 16 ? qb + G::S * (k - 8) : G::M);
-                    const float2 x = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : xn);
-                    float2 gy = k < 8 ? ga[k] : (k < 16 ? gb[k - 8] : gn);
+                for (int k = 0; k < 9; ++k) {
+                    if (k == 8 && (half != 0 || p != 0)) continue;
+                    const int bin = k < 8 ? q + G::S * k : G::M;
+                    const float2 x = k < 8 ? (half ? xb[k] : xa[k]) : xn;
+                    float2 gy = k < 8 ? (half ? gb[k] : ga[k]) : gn;
                     // iSTFT adjoint: c_k / n with the 2/n folded into the window -> edges get 1/2, real only
-                    if (p == 0 && (k == 0 || k == 16)) gy = make_float2(0.5f * gy.x, 0.f);
+                    if (p == 0 && half == 0 && (k == 0 || k == 8)) gy = make_float2(0.5f * gy.x, 0.f);
                     const size_t idx = ((size_t)row * G::F + bin) * (size_t)a.nframe + t;
-                    if (a.mode == 0) {
-                        float m = __ldg(a.mask + idx);
-                        if (a.pre_tanh) m = tanhf(m);
-                        float gm = x.x * gy.x + x.y * gy.y;
-                        if (a.pre_tanh) gm *= (1.f - m * m);
-                        a.out[idx] = gm;
-                    } else {
-                        float2 m = __ldg(reinterpret_cast<const float2*>(a.mask) + idx);
-                        if (a.pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
-                        float2 gm, gx;
-                        MaskMath::bwd(a.mode, x, m, gy, gm, gx);
-                        if (a.pre_tanh) gm = make_float2(gm.x * (1.f - m.x * m.x), gm.y * (1.f - m.y * m.y));
-                        reinterpret_cast<float2*>(a.out)[idx] = gm;
-                    }
+                    float2 gm, gx;
+                    MaskMath::grad<MODE, TANH>(x, k < 8 ? m[k] : mn, gy, gm, gx);
+                    if (MODE == 0) a.out[idx] = gm.x;
+                    else reinterpret_cast<float2*>(a.out)[idx] = gm;
                 }
             }
         }

@@ -69,32 +69,66 @@ __device__ __forceinline__ float inv_env_at(const Tables& tb, int T, int i) {
 }
 
 // Fill the hop-row-padded stage with padded coordinates [p0, p0 + SROWS*HOP).
+// All global loads of a thread are issued back to back into registers before the first store, so a
+// fill costs ONE memory round trip instead of one per loop iteration (ncu: the store that waited on
+// the load held 90 % of the long-scoreboard samples before this change).
 template <class G, int LMODE>
 __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const float* __restrict__ src,
                                            int p0, const AnaArgs& a, int tid) {
-    for (int rel = 2 * tid; rel < G::SROWS * G::HOP; rel += 2 * G::NT) {
-        const int i = p0 + rel;
-        float v0, v1;
-        if (LMODE == LOAD_REFLECT) {
-            const int j = i - G::N / 2;
-            if (j >= 0 && j + 1 < a.nsample) {
-                v0 = __ldg(src + j);
-                v1 = __ldg(src + j + 1);
-            } else {
-                v0 = sample_reflect(src, G::N / 2, a.nsample, G::N, i);
-                v1 = sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1);
+    constexpr int SLOTS = G::SROWS * G::HOP / 2;                 // float2 slots
+    constexpr int K = (SLOTS + G::NT - 1) / G::NT;
+    float2 v[K];
+    const int base = (LMODE == LOAD_ZEROPAD) ? p0 - a.pad : p0 - G::N / 2;   // source index of slot 0
+    const int limit = (LMODE == LOAD_ENV) ? a.in_len : a.nsample;
+    const bool interior = base >= 0 && base + 2 * SLOTS <= limit &&
+                          (LMODE != LOAD_ENV || p0 + 2 * SLOTS <= a.nsample);
+    if (interior) {                                              // uniform per CTA: plain streaming loads
+        if ((reinterpret_cast<uintptr_t>(src + base) & 7) == 0) {
+            const float2* s2 = reinterpret_cast<const float2*>(src + base);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int slot = tid + k * G::NT;
+                if (slot < SLOTS) v[k] = __ldg(s2 + slot);
             }
-        } else if (LMODE == LOAD_ZEROPAD) {
-            const int j = i - a.pad;
-            v0 = (j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f;
-            v1 = (j + 1 >= 0 && j + 1 < a.nsample) ? __ldg(src + j + 1) : 0.f;
-        } else {   // LOAD_ENV: gy / envelope placed at n/2 inside the natural padded length
-            const int s = i - G::N / 2;
-            v0 = (s >= 0 && s < a.in_len && i < a.nsample) ? __ldg(src + s) * inv_env_at<G>(a.tb, a.nframe, i) : 0.f;
-            v1 = (s + 1 >= 0 && s + 1 < a.in_len && i + 1 < a.nsample)
-                     ? __ldg(src + s + 1) * inv_env_at<G>(a.tb, a.nframe, i + 1) : 0.f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int slot = tid + k * G::NT;
+                if (slot < SLOTS) v[k] = make_float2(__ldg(src + base + 2 * slot), __ldg(src + base + 2 * slot + 1));
+            }
         }
-        *reinterpret_cast<float2*>(stage + (rel / G::HOP) * G::SROW + rel % G::HOP) = make_float2(v0, v1);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int slot = tid + k * G::NT;
+            if (slot >= SLOTS) continue;
+            const int i = p0 + 2 * slot;
+            if (LMODE == LOAD_REFLECT) {
+                v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i),
+                                   sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1));
+            } else if (LMODE == LOAD_ZEROPAD) {
+                const int j = i - a.pad;
+                v[k] = make_float2((j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f,
+                                   (j + 1 >= 0 && j + 1 < a.nsample) ? __ldg(src + j + 1) : 0.f);
+            } else {
+                const int q = i - G::N / 2;
+                v[k] = make_float2((q >= 0 && q < a.in_len && i < a.nsample) ? __ldg(src + q) : 0.f,
+                                   (q + 1 >= 0 && q + 1 < a.in_len && i + 1 < a.nsample) ? __ldg(src + q + 1) : 0.f);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int slot = tid + k * G::NT;
+        if (slot >= SLOTS) continue;
+        const int rel = 2 * slot;
+        float2 w = v[k];
+        if (LMODE == LOAD_ENV) {      // gy / envelope (zero where the envelope is empty)
+            const int i = p0 + rel;
+            w.x *= inv_env_at<G>(a.tb, a.nframe, i);
+            w.y *= inv_env_at<G>(a.tb, a.nframe, i + 1);
+        }
+        *reinterpret_cast<float2*>(stage + (rel / G::HOP) * G::SROW + rel % G::HOP) = w;
     }
 }
 
@@ -402,10 +436,11 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
                     } else if (t < a.nframe && !(k == 16 && p != 0)) {
                         const float ca = fmaxf(pw, SE_MRSTFT_CLAMP);
                         const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
-                        const float d = sqrtf(cb) - sqrtf(ca);
+                        const float d = cb * rsqrtf(cb) - ca * rsqrtf(ca);
                         s_d2 += d * d;
                         s_b2 += cb;
-                        s_lm += 0.5f * fabsf(logf(cb) - logf(ca));
+                        // |log b - log a| = ln2/2 |log2(cb/ca)|
+                        s_lm += 0.34657359f * fabsf(__log2f(__fdividef(cb, ca)));
                     }
                 }
             }
@@ -477,9 +512,11 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
                         const float pa = v.x * v.x + v.y * v.y;
                         float coef = 0.f;
                         if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
-                            const float ma = sqrtf(pa), mb = sqrtf(fmaxf(pb[i][k], SE_MRSTFT_CLAMP));
+                            const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
+                            const float ia = rsqrtf(pa);
+                            const float ma = pa * ia, mb = cb * rsqrtf(cb);
                             const float sg = ma > mb ? 1.f : (ma < mb ? -1.f : 0.f);
-                            coef = (alpha * (ma - mb) + beta * sg / ma) / ma;
+                            coef = alpha * (ma - mb) * ia + beta * sg * ia * ia;
                         }
                         // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
                         if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
@@ -530,36 +567,58 @@ __global__ void k_loss_value(const double* __restrict__ sums, double c0, double 
 }
 
 // ------------------------------------------------------------------ masks (elementwise)
-struct MaskMath {
-    // y = f(x, m); m already squashed.  E: tanh(|m|) sqrt(|x|^2+1e-8) (x/|x|)(m/|m|)
-    __device__ static __forceinline__ float2 unit(float2 v, float p) {
-        if (p > 1e-30f) { const float r = 1.0f / sqrtf(p); return make_float2(v.x * r, v.y * r); }
-        const float s = fmaxf(fabsf(v.x), fabsf(v.y));
-        if (s == 0.f) return make_float2(1.f, 0.f);
-        const float ax = v.x / s, ay = v.y / s;
-        const float r = 1.0f / sqrtf(ax * ax + ay * ay);
-        return make_float2(ax * r, ay * r);
+// The bin ops are issue-bound (ncu: the precise-libm 'E' mask ran at 82 % issue utilisation and
+// only 54 % of HBM), so they use MUFU-based forms whose error (<= 4e-7 relative) sits two orders
+// below the 1e-4 budget: rsqrt for 1/|z| and sqrt, exp-based tanh with a series below 0.3.
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float ax = fabsf(x);
+    if (ax < 0.3f) {
+        const float x2 = x * x;
+        return x * (1.f + x2 * (-0.33333334f + x2 * (0.13333334f + x2 * (-0.053968254f + x2 * 0.021869488f))));
     }
-    __device__ static __forceinline__ float2 fwd(int mode, float2 x, float2 m) {
-        if (mode == 2) return cmul(x, m);
-        if (mode == 3) return make_float2(x.x * m.x, x.y * m.y);
+    const float r = 1.f - __fdividef(2.f, __expf(2.f * ax) + 1.f);      // exp overflow -> r = 1
+    return copysignf(r, x);
+}
+
+struct MaskMath {
+    // unit vector of v (p = |v|^2); (1,0) at the origin like atan2(0,0) = 0
+    __device__ static __forceinline__ float2 unit(float2 v, float p) {
+        // branch-free: rescale (exactly, by 2^60) when |v|^2 would underflow, so the phase of tiny
+        // non-zero values survives like it does through atan2
+        const float sc = p < 1e-30f ? 1.15292150460684698e18f : 1.f;
+        const float vx = v.x * sc, vy = v.y * sc;
+        const float p2 = vx * vx + vy * vy;
+        const float r = rsqrtf(fmaxf(p2, 1e-37f));
+        return p2 > 0.f ? make_float2(vx * r, vy * r) : make_float2(1.f, 0.f);
+    }
+    // y = f(x, m); m already squashed.  E: tanh(|m|) sqrt(|x|^2+1e-8) (x/|x|)(m/|m|)
+    template <int MODE>
+    __device__ static __forceinline__ float2 fwd(float2 x, float2 m) {
+        if (MODE == 2) return cmul(x, m);
+        if (MODE == 3) return make_float2(x.x * m.x, x.y * m.y);
         const float px = x.x * x.x + x.y * x.y, pm = m.x * m.x + m.y * m.y;
         const float2 ux = unit(x, px), um = unit(m, pm);
-        const float gain = tanhf(sqrtf(pm)) * sqrtf(px + 1e-8f);
+        const float pe = px + 1e-8f;
+        const float r = pm > 0.f ? pm * rsqrtf(pm) : 0.f;
+        const float gain = fast_tanh(r) * (pe * rsqrtf(pe));
         const float2 u = cmul(ux, um);
         return make_float2(gain * u.x, gain * u.y);
     }
-    // gradient wrt m (squashed) and optionally x, given gy
-    __device__ static __forceinline__ void bwd(int mode, float2 x, float2 m, float2 gy, float2& gm, float2& gx) {
-        if (mode == 2) { gm = cmulc(gy, x); gx = cmulc(gy, m); return; }
-        if (mode == 3) { gm = make_float2(x.x * gy.x, x.y * gy.y); gx = make_float2(m.x * gy.x, m.y * gy.y); return; }
+    // gradient wrt m (squashed) and x, given gy
+    template <int MODE>
+    __device__ static __forceinline__ void bwd(float2 x, float2 m, float2 gy, float2& gm, float2& gx) {
+        if (MODE == 2) { gm = cmulc(gy, x); gx = cmulc(gy, m); return; }
+        if (MODE == 3) { gm = make_float2(x.x * gy.x, x.y * gy.y); gx = make_float2(m.x * gy.x, m.y * gy.y); return; }
         const float px = x.x * x.x + x.y * x.y, pm = m.x * m.x + m.y * m.y;
         const float2 ux = unit(x, px), um = unit(m, pm);
-        const float mag = sqrtf(px + 1e-8f), r = sqrtf(pm), th = tanhf(r);
+        const float pe = px + 1e-8f;
+        const float mag = pe * rsqrtf(pe);
+        const float ir = pm > 0.f ? rsqrtf(pm) : 0.f;
+        const float r = pm * ir, th = fast_tanh(r);
         // h = phi(r) m, phi = tanh(r)/r ; y = (mag ux) * h
         float phi, dphi_r;                       // dphi_r = phi'(r) / r
         if (r < 0.05f) { phi = 1.f - pm * (1.f / 3.f) + pm * pm * (2.f / 15.f); dphi_r = -2.f / 3.f + pm * (8.f / 15.f); }
-        else { phi = th / r; dphi_r = ((1.f - th * th) * r - th) / (r * pm); }
+        else { phi = th * ir; dphi_r = ((1.f - th * th) * r - th) * ir * ir * ir; }
         const float2 cx = make_float2(mag * ux.x, mag * ux.y);
         const float2 gh = cmulc(gy, cx);         // conj(cx) * gy
         const float dot = m.x * gh.x + m.y * gh.y;
@@ -568,52 +627,58 @@ struct MaskMath {
         const float2 h = make_float2(th * um.x, th * um.y);
         const float2 gk = cmulc(gy, h);
         if (px > 1e-30f) {
-            const float rho = sqrtf(px), psi = mag / rho, dpsi_r = -1e-8f / (rho * px * mag);
+            const float irho = rsqrtf(px), psi = mag * irho, dpsi_r = -1e-8f * irho * irho * irho / mag;
             const float dx = x.x * gk.x + x.y * gk.y;
             gx = make_float2(psi * gk.x + dpsi_r * dx * x.x, psi * gk.y + dpsi_r * dx * x.y);
         } else gx = make_float2(0.f, 0.f);
     }
+    // one complex bin, runtime-free: MODE 0 keeps the real mask in m.x
+    template <int MODE, bool TANH>
+    __device__ static __forceinline__ float2 apply(float2 x, float2 m) {
+        if (MODE == 0) { const float g = TANH ? fast_tanh(m.x) : m.x; return make_float2(x.x * g, x.y * g); }
+        if (TANH) m = make_float2(fast_tanh(m.x), fast_tanh(m.y));
+        return fwd<MODE>(x, m);
+    }
+    // gradient wrt the RAW mask (MODE 0: result in .x) and wrt x
+    template <int MODE, bool TANH>
+    __device__ static __forceinline__ void grad(float2 x, float2 m, float2 gy, float2& gm, float2& gx) {
+        if (MODE == 0) {
+            const float g = TANH ? fast_tanh(m.x) : m.x;
+            float d = x.x * gy.x + x.y * gy.y;
+            if (TANH) d *= (1.f - g * g);
+            gm = make_float2(d, 0.f);
+            gx = make_float2(gy.x * g, gy.y * g);
+            return;
+        }
+        if (TANH) m = make_float2(fast_tanh(m.x), fast_tanh(m.y));
+        bwd<MODE>(x, m, gy, gm, gx);
+        if (TANH) gm = make_float2(gm.x * (1.f - m.x * m.x), gm.y * (1.f - m.y * m.y));
+    }
 };
 
-__global__ void __launch_bounds__(256) k_mask_fwd(const float2* __restrict__ spec, const float* __restrict__ mask,
-                                                  float2* __restrict__ out, int64_t count, int mode, int pre_tanh) {
+template <int MODE, bool TANH>
+__global__ void __launch_bounds__(256) k_mask_fwd_t(const float2* __restrict__ spec, const float* __restrict__ mask,
+                                                    float2* __restrict__ out, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         const float2 x = __ldg(spec + i);
-        if (mode == 0) {
-            float m = __ldg(mask + i);
-            if (pre_tanh) m = tanhf(m);
-            out[i] = make_float2(x.x * m, x.y * m);
-        } else {
-            float2 m = __ldg(reinterpret_cast<const float2*>(mask) + i);
-            if (pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
-            out[i] = MaskMath::fwd(mode, x, m);
-        }
+        const float2 m = MODE == 0 ? make_float2(__ldg(mask + i), 0.f) : __ldg(reinterpret_cast<const float2*>(mask) + i);
+        out[i] = MaskMath::apply<MODE, TANH>(x, m);
     }
 }
 
-__global__ void __launch_bounds__(256) k_mask_bwd(const float2* __restrict__ spec, const float* __restrict__ mask,
-                                                  const float2* __restrict__ gout, float* __restrict__ gmask,
-                                                  float2* __restrict__ gspec, int64_t count, int mode, int pre_tanh) {
+template <int MODE, bool TANH>
+__global__ void __launch_bounds__(256) k_mask_bwd_t(const float2* __restrict__ spec, const float* __restrict__ mask,
+                                                    const float2* __restrict__ gout, float* __restrict__ gmask,
+                                                    float2* __restrict__ gspec, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
         const float2 x = __ldg(spec + i), gy = __ldg(gout + i);
-        if (mode == 0) {
-            float m = __ldg(mask + i);
-            if (pre_tanh) m = tanhf(m);
-            float gm = x.x * gy.x + x.y * gy.y;
-            if (pre_tanh) gm *= (1.f - m * m);
-            gmask[i] = gm;
-            if (gspec) gspec[i] = make_float2(gy.x * m, gy.y * m);
-        } else {
-            float2 m = __ldg(reinterpret_cast<const float2*>(mask) + i);
-            if (pre_tanh) m = make_float2(tanhf(m.x), tanhf(m.y));
-            float2 gm, gx;
-            MaskMath::bwd(mode, x, m, gy, gm, gx);
-            if (pre_tanh) gm = make_float2(gm.x * (1.f - m.x * m.x), gm.y * (1.f - m.y * m.y));
-            reinterpret_cast<float2*>(gmask)[i] = gm;
-            if (gspec) gspec[i] = gx;
-        }
+        const float2 m = MODE == 0 ? make_float2(__ldg(mask + i), 0.f) : __ldg(reinterpret_cast<const float2*>(mask) + i);
+        float2 gm, gx;
+        MaskMath::grad<MODE, TANH>(x, m, gy, gm, gx);
+        if (MODE == 0) gmask[i] = gm.x; else reinterpret_cast<float2*>(gmask)[i] = gm;
+        if (gspec) gspec[i] = gx;
     }
 }
 

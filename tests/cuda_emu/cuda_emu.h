@@ -150,3 +150,9 @@ static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline void __threadfence() {}
+static inline float emu_expf(float x) { return std::exp(x); }
+static inline float emu_logf(float x) { return std::log(x); }
+static inline float emu_log2f(float x) { return std::log2(x); }
+#define __expf emu_expf
+#define __logf emu_logf
+#define __log2f emu_log2f
