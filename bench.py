@@ -205,7 +205,7 @@ def run_ours(args):
     def k_istft(): nv.check(L.se_istft_fwd(P(Y), P(y), rows, T, N, N_FFT, HOP, WIN, float(WIN), st))
     def k_loss_fwd(clean): nv.check(L.se_mrstft_loss_fwd(P(y), P(clean), rows, N, P(sums), P(ws), st))
     def k_loss_val(): nv.check(L.se_mrstft_loss_value(P(sums), rows * world, N, P(loss), st))
-    def k_loss_bwd(clean): nv.check(L.se_mrstft_loss_bwd(P(y), P(clean), P(sums), P(one), rows * world, rows, N, P(gy), st))
+    def k_loss_bwd(clean): nv.check(L.se_mrstft_loss_bwd(P(y), P(ws), P(sums), P(one), rows * world, rows, N, P(gy), st))
     def k_istft_bwd(): nv.check(L.se_istft_bwd(P(gy), P(gY), rows, T, N, N_FFT, HOP, WIN, float(WIN), st))
     def k_mask_bwd(raw): nv.check(L.se_mask_bwd(P(X), P(raw), P(gY), P(graw), 0, count, 1, 1, st))
     def k_enh_fwd(x, raw): nv.check(L.se_enhance_fwd(P(x), P(raw), P(y), rows, N, N_FFT, HOP, WIN, 1, 1, st))
@@ -276,6 +276,7 @@ def run_ours(args):
     kernels = []
     if rank == 0 and not args.no_breakdown:
         S_, P_, M_ = 4.0 * N, 8.0 * F * T, 8.0 * F * T
+        R_ = 4.0 * sum((n // 2 + 1) * (1 + N // h) for n, h in RES)     # |B| saved by loss fwd, read by loss bwd
         flop_fft = lambda n, h: 2.5 * n * (n.bit_length() - 1) * (1 + N // h)
         f1024 = flop_fft(N_FFT, HOP)
         f_all = sum(flop_fft(n, h) for n, h in RES)
@@ -285,8 +286,8 @@ def run_ours(args):
             ("stft_fwd", lambda i: k_stft(sets[i & 1][0]), S_ + P_, f1024, 1),
             ("mask_fwd", lambda i: k_mask(sets[i & 1][2]), 2 * P_ + M_, 0, 1),
             ("istft_fwd", lambda i: k_istft(), P_ + S_, f1024, 1),
-            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 3 * 2 * S_, 2 * f_all, 6),
-            ("mrstft_loss_bwd(3 res)", lambda i: k_loss_bwd(sets[i & 1][1]), 3 * 3 * S_, 3 * f_all, 3),
+            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 6),
+            ("mrstft_loss_bwd(3 res)", lambda i: k_loss_bwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 3),
             ("istft_bwd", lambda i: k_istft_bwd(), S_ + P_, f1024, 1),
             ("mask_bwd", lambda i: k_mask_bwd(sets[i & 1][2]), 2 * P_ + 2 * M_, 0, 1),
         ]

@@ -86,15 +86,18 @@ int se_mask_bwd(const float* spec, const float* mask, const float* gout, float* 
  * (512,128,512) (1024,256,1024) (2048,512,2048).
  *   fwd   : est, ref [rows,N] -> sums[9] (device, double): per resolution
  *           sum (b-a)^2, sum b^2, sum |log b - log a|.  Deterministic two-stage reduction.
- *           workspace: se_mrstft_workspace_bytes(rows, nsample) bytes of device scratch.
+ *           workspace: se_mrstft_workspace_bytes(rows, nsample) bytes of device scratch; the
+ *           forward pass also leaves the clamped reference magnitudes |B| there, so the backward
+ *           pass transforms only the estimate.  Keep it alive (unmodified) until bwd has run.
  *   value : sums (after the caller all-reduced them across ranks) -> loss (device float).
  *           global_rows = rows summed over ranks (sets the mean's denominator).
- *   bwd   : g_est [rows,N] = gout * dloss/dest, gout a DEVICE scalar (upstream gradient). */
+ *   bwd   : g_est [rows,N] = gout * dloss/dest, gout a DEVICE scalar (upstream gradient);
+ *           workspace = the buffer the matching fwd call filled. */
 int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample);
 int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums,
                        void* workspace, void* stream);
 int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsample, float* loss, void* stream);
-int se_mrstft_loss_bwd(const float* est, const float* ref, const double* sums, const float* gout,
+int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* sums, const float* gout,
                        int64_t global_rows, int64_t rows, int64_t nsample, float* g_est, void* stream);
 
 /* ---- fused wave -> STFT -> mask -> iSTFT -> wave (stft_custom + model tail + istft_custom in

@@ -306,12 +306,12 @@ __device__ __forceinline__ void passA_inv_task(const float2* __restrict__ zb, co
 // SEG float2 each; output block b = frame index gets segment q of frame b - q.  Contributions
 // that wrap around the 16-lane group belong to the NEXT group's first OLA-1 blocks: they are
 // returned in `carry` (registers) and added there.  acc[s] is block `fr`, offset 2*(u + 64 s).
-template <class G>
+template <class G, bool CARRY = true>
 __device__ __forceinline__ void ola_rotate(const float2* a, int fr, float2* carry, float2* acc) {
     float2 nc[G::SEG];
 #pragma unroll
     for (int s = 0; s < G::SEG; ++s) {
-        acc[s] = cadd(a[s], carry[s]);
+        acc[s] = CARRY ? cadd(a[s], carry[s]) : a[s];
         nc[s] = make_float2(0.f, 0.f);
     }
 #pragma unroll
@@ -321,11 +321,13 @@ __device__ __forceinline__ void ola_rotate(const float2* a, int fr, float2* carr
             const float rx = __shfl_sync(0xffffffffu, a[q * G::SEG + s].x, (fr - q) & 15, 16);
             const float ry = __shfl_sync(0xffffffffu, a[q * G::SEG + s].y, (fr - q) & 15, 16);
             if (fr >= q) { acc[s].x += rx; acc[s].y += ry; }
-            else         { nc[s].x += rx;  nc[s].y += ry; }
+            else if (CARRY) { nc[s].x += rx; nc[s].y += ry; }
         }
     }
+    if (CARRY) {
 #pragma unroll
-    for (int s = 0; s < G::SEG; ++s) carry[s] = nc[s];
+        for (int s = 0; s < G::SEG; ++s) carry[s] = nc[s];
+    }
 }
 
 }  // namespace se

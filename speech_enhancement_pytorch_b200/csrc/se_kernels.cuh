@@ -20,6 +20,12 @@ struct Tables {
     const float* inv_env;   // 1 / sum_q w2[o + q*HOP], HOP floats
 };
 
+__device__ __forceinline__ Tables launder_tables(const Tables& t) {
+    Tables r;
+    r.win = launder(t.win); r.tw = launder(t.tw); r.twn = launder(t.twn); r.w2 = launder(t.w2); r.inv_env = launder(t.inv_env);
+    return r;
+}
+
 struct AnaArgs {            // analysis: waveform-like -> spectrum
     Tables tb;
     const float* in;        // [rows, in_len]
@@ -209,7 +215,8 @@ __device__ __forceinline__ void synthesis_task(float2* zb, const Tables& tb, int
     passC_inv_unit<G>(zb, task_qa<G>(p), fr, ya);
     passC_inv_unit<G>(zb, task_qb<G>(p), fr, yb);
 }
-template <class G>
+// CARRY=false: single-group chunks -- the wrapped contributions belong to blocks nobody emits
+template <class G, bool CARRY = true>
 __device__ __forceinline__ void synthesis_tail(float2* zb, const Tables& tb, float* ostage, int unit, int fr,
                                                float2 (*carry)[G::SEG]) {
     __syncthreads();
@@ -220,7 +227,7 @@ __device__ __forceinline__ void synthesis_tail(float2* zb, const Tables& tb, flo
         const int u = unit + i * G::NU;
         float2 v[G::R1], acc[G::SEG];
         passA_inv_task<G>(zb, tb.win, tb.tw, u, fr, v);
-        ola_rotate<G>(v, fr, carry[i], acc);
+        ola_rotate<G, CARRY>(v, fr, CARRY ? carry[i] : nullptr, acc);
 #pragma unroll
         for (int s = 0; s < G::SEG; ++s)
             *reinterpret_cast<float2*>(ostage + fr * G::SROW + 2 * (u + 64 * s)) = acc[s];
@@ -390,6 +397,7 @@ struct LossArgs {
     const float* ref;
     float* g_est;            // bwd
     double* partials;        // fwd: [grid][3]
+    float* refmag;           // fwd writes / bwd reads |B| (clamped) as [rows][F][T] for this resolution
     const double* sums;      // bwd: this resolution's 3 sums
     const float* gout;       // bwd: device scalar
     int nsample, nframe;
@@ -419,20 +427,26 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
         float pb[G::TC][17];
 #pragma unroll 1
         for (int sig = 0; sig < 2; ++sig) {              // 0: reference magnitudes, 1: estimate + statistics
+            const Tables tb = launder_tables(a.tb);
             fill_stage<G, LOAD_REFLECT>(stage, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
             __syncthreads();
-            analysis_passes<G>(stage, a.tb, zb, unit, fr);
+            analysis_passes<G>(stage, tb, zb, unit, fr);
 #pragma unroll
             for (int i = 0; i < G::TC; ++i) {
                 const int p = unit + i * G::NU;
                 float2 xa[8], xb[8], nyq;
-                analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+                analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
 #pragma unroll
                 for (int k = 0; k < 17; ++k) {
                     const float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
                     const float pw = v.x * v.x + v.y * v.y;
                     if (sig == 0) {
                         pb[i][k] = pw;
+                        if (t < a.nframe && !(k == 16 && p != 0)) {      // keep |B| for the backward pass
+                            const float cb = fmaxf(pw, SE_MRSTFT_CLAMP);
+                            const int bin = k < 8 ? task_qa<G>(p) + G::S * k : (k < 16 ? task_qb<G>(p) + G::S * (k - 8) : G::M);
+                            a.refmag[((size_t)row * G::F + bin) * (size_t)a.nframe + t] = cb * rsqrtf(cb);
+                        }
                     } else if (t < a.nframe && !(k == 16 && p != 0)) {
                         const float ca = fmaxf(pw, SE_MRSTFT_CLAMP);
                         const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
@@ -479,56 +493,48 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
     const float beta = gs * a.inv_count;
     float* gx_row = a.g_est + (size_t)row * a.nsample;
-    float2 carry[G::TA][G::SEG];
-#pragma unroll
-    for (int i = 0; i < G::TA; ++i)
-#pragma unroll
-        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
+    // chunks are planned as single groups (<= 16 - (OLA-1) emitted blocks): no OLA carry to keep live
     for (int g = 0; g < c.ngroups; ++g) {
         const int f_base = c.f0 + g * G::FR;
         const int t = f_base + fr;
         const bool live = (t >= 0 && t < a.nframe);
-        float pb[G::TC][17];
-#pragma unroll 1
-        for (int sig = 0; sig < 2; ++sig) {              // 0: reference magnitudes, 1: estimate -> gradient spectrum
-            fill_stage<G, LOAD_REFLECT>(iobuf, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
-            __syncthreads();
-            analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
+        const int tc = live ? t : 0;
+        const float* mrow = a.refmag + (size_t)row * G::F * a.nframe + tc;
+        fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+        __syncthreads();
+        analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
 #pragma unroll
-            for (int i = 0; i < G::TC; ++i) {
-                const int p = unit + i * G::NU;
-                float2 xa[8], xb[8], nyq;
-                analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
-                if (sig == 0) {
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+            float mb[17];                                    // |B| saved by the forward pass
 #pragma unroll
-                    for (int k = 0; k < 17; ++k) {
-                        const float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
-                        pb[i][k] = v.x * v.x + v.y * v.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 17; ++k) {
-                        float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
-                        const float pa = v.x * v.x + v.y * v.y;
-                        float coef = 0.f;
-                        if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
-                            const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
-                            const float ia = rsqrtf(pa);
-                            const float ma = pa * ia, mb = cb * rsqrtf(cb);
-                            const float sg = ma > mb ? 1.f : (ma < mb ? -1.f : 0.f);
-                            coef = alpha * (ma - mb) * ia + beta * sg * ia * ia;
-                        }
-                        // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
-                        if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
-                        v = make_float2(v.x * coef, v.y * coef);
-                        if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
-                    }
-                    synthesis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
-                }
+            for (int k = 0; k < 8; ++k) {
+                mb[k] = __ldg(mrow + (size_t)(qa + G::S * k) * a.nframe);
+                mb[8 + k] = __ldg(mrow + (size_t)(qb + G::S * k) * a.nframe);
             }
-            if (sig == 0) __syncthreads();               // pass C reads of zb done before the next pass A writes
+            mb[16] = __ldg(mrow + (size_t)G::M * a.nframe);
+            float2 xa[8], xb[8], nyq;
+            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+#pragma unroll
+            for (int k = 0; k < 17; ++k) {
+                float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                const float pa = v.x * v.x + v.y * v.y;
+                float coef = 0.f;
+                if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
+                    const float ia = rsqrtf(pa);
+                    const float ma = pa * ia;
+                    const float sg = ma > mb[k] ? 1.f : (ma < mb[k] ? -1.f : 0.f);
+                    coef = alpha * (ma - mb[k]) * ia + beta * sg * ia * ia;
+                }
+                // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
+                if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
+                v = make_float2(v.x * coef, v.y * coef);
+                if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
+            }
+            synthesis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
         }
-        synthesis_tail<G>(zb, a.tb, iobuf, unit, fr, carry);
+        synthesis_tail<G, false>(zb, a.tb, iobuf, unit, fr, nullptr);
         emit_adj<G>(iobuf, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
         __syncthreads();
     }

@@ -22,6 +22,16 @@
 
 namespace se {
 
+// Opaque pointer copy: stops the compiler from hoisting table loads out of a loop (they would
+// otherwise be kept live in registers across whole passes and spill).
+template <class T>
+__device__ __forceinline__ T* launder(T* p) {
+#ifndef SE_EMULATE
+    asm volatile("" : "+l"(p));
+#endif
+    return p;
+}
+
 template <class... Params, class... Args>
 inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block, size_t smem,
                           cudaStream_t stream, Args... args) {

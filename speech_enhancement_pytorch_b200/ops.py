@@ -161,18 +161,18 @@ class _MRSTFT(torch.autograd.Function):
                 dist.all_reduce(sums, group=group)
                 global_rows = global_rows_hint or rows * dist.get_world_size(group)
             nv.check(L.se_mrstft_loss_value(sums.data_ptr(), global_rows, n, loss.data_ptr(), st))
-        ctx.save_for_backward(est, ref, sums)
+        ctx.save_for_backward(est, ws, sums)
         ctx.global_rows = global_rows
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        est, ref, sums = ctx.saved_tensors
+        est, ws, sums = ctx.saved_tensors
         rows, n = est.shape
         gout = gout.contiguous().float()
         g = torch.empty_like(est)
         with nv.on_device(est.device):
-            nv.check(nv.lib().se_mrstft_loss_bwd(est.data_ptr(), ref.data_ptr(), sums.data_ptr(), gout.data_ptr(),
+            nv.check(nv.lib().se_mrstft_loss_bwd(est.data_ptr(), ws.data_ptr(), sums.data_ptr(), gout.data_ptr(),
                                                  ctx.global_rows, rows, n, g.data_ptr(), nv.stream_ptr(est.device)))
         return g, None, None, None
 

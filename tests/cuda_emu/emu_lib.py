@@ -117,14 +117,16 @@ def mrstft_fwd(est, ref):
     check(lib().se_mrstft_loss_fwd(ptr(est), ptr(ref), i64(rows), i64(N), ptr(sums), ptr(ws), None))
     loss = np.full(1, np.nan, np.float32)
     check(lib().se_mrstft_loss_value(ptr(sums), i64(rows), i64(N), ptr(loss), None))
+    mrstft_fwd.workspace = ws
     return sums, float(loss[0])
 
 
 def mrstft_bwd(est, ref, sums, gout=1.0):
+    ws = mrstft_fwd.workspace
     rows, N = est.shape
     g = np.full((rows, N), np.nan, np.float32)
     go = np.array([gout], np.float32)
-    check(lib().se_mrstft_loss_bwd(ptr(est), ptr(ref), ptr(sums), ptr(go), i64(rows), i64(rows), i64(N), ptr(g), None))
+    check(lib().se_mrstft_loss_bwd(ptr(est), ptr(ws), ptr(sums), ptr(go), i64(rows), i64(rows), i64(N), ptr(g), None))
     return g
 
 
