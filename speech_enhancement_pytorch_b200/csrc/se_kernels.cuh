@@ -7,6 +7,11 @@
 #pragma once
 #include "se_fft.cuh"
 
+// pass-C task loop: tasks share no state, so rolling it halves code size and register pressure
+#ifndef SE_TC_PRAGMA
+#define SE_TC_PRAGMA _Pragma("unroll 1")
+#endif
+
 namespace se {
 
 enum LoadMode { LOAD_REFLECT = 0, LOAD_ZEROPAD = 1, LOAD_ENV = 2 };
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
         __syncthreads();
         analysis_passes<G>(stage, a.tb, zb, unit, fr);
         const int t = f_base + fr;
-#pragma unroll
+        SE_TC_PRAGMA
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
             float2 xa[8], xb[8], nyq;
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
     for (int g = 0; g < c.ngroups; ++g) {
         const int f_base = c.f0 + g * G::FR;
         const int t = f_base + fr;
-#pragma unroll
+        SE_TC_PRAGMA
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
             float2 ya[8], yb[8], nyq;
@@ -500,10 +505,23 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         const bool live = (t >= 0 && t < a.nframe);
         const int tc = live ? t : 0;
         const float* mrow = a.refmag + (size_t)row * G::F * a.nframe + tc;
+        // |B| is consumed after two passes: start pulling its lines towards L2 now (fr == 0 covers the
+        // 64-byte run of 16 frames; the neighbouring lane group shares the line)
+        if (fr == 0 || fr == 8) {
+#pragma unroll
+            for (int i = 0; i < G::TC; ++i) {
+                const int p = unit + i * G::NU;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    prefetch_l2(mrow + (size_t)(task_qa<G>(p) + G::S * k) * a.nframe);
+                    prefetch_l2(mrow + (size_t)(task_qb<G>(p) + G::S * k) * a.nframe);
+                }
+            }
+        }
         fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
         __syncthreads();
         analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
-#pragma unroll
+        SE_TC_PRAGMA
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
             const int qa = task_qa<G>(p), qb = task_qb<G>(p);

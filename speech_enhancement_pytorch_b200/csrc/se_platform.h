@@ -32,6 +32,15 @@ __device__ __forceinline__ T* launder(T* p) {
     return p;
 }
 
+// L2 prefetch of a line that will be read later in the kernel (no register cost)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef SE_EMULATE
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 template <class... Params, class... Args>
 inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block, size_t smem,
                           cudaStream_t stream, Args... args) {
