@@ -167,6 +167,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L = nv.lib()
@@ -227,7 +229,7 @@ def run_ours(args):
         else:
             k_istft_bwd(); k_mask_bwd(raw)
 
-    n_launch = (2 if use_fused else 5) + 6 + 1 + 3      # + 3 loss fwd, 3 reduce, value, 3 loss bwd
+    n_launch = (2 if use_fused else 5) + 4 + 1 + 3      # + 3 loss fwd, 1 reduce, value, 3 loss bwd
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -286,7 +288,7 @@ def run_ours(args):
             ("stft_fwd", lambda i: k_stft(sets[i & 1][0]), S_ + P_, f1024, 1),
             ("mask_fwd", lambda i: k_mask(sets[i & 1][2]), 2 * P_ + M_, 0, 1),
             ("istft_fwd", lambda i: k_istft(), P_ + S_, f1024, 1),
-            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 6),
+            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 4),
             ("mrstft_loss_bwd(3 res)", lambda i: k_loss_bwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 3),
             ("istft_bwd", lambda i: k_istft_bwd(), S_ + P_, f1024, 1),
             ("mask_bwd", lambda i: k_mask_bwd(sets[i & 1][2]), 2 * P_ + 2 * M_, 0, 1),

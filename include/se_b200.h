@@ -56,6 +56,15 @@ const char* se_last_error(void);
 int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop,
                 int win_length, float scale, void* stream);
 
+/* ---- evaluate()'s "segment then STFT" (src/evaluate.py:29-39,164-183) without materialising the
+ * overlapping segments: x [nclip, clip_stride] holds clips of clip_len valid samples; segment s of
+ * clip c is x[c, s*seg_stride : s*seg_stride + nsample] (zero beyond clip_len, like the reference's
+ * zero-filled pad) and is reflect-padded on its own.  spec [(nseg*nclip), F, T, 2], row = s*nclip + c
+ * (the reference's reshape(num_segment*nbatch, nchannel, ...) order). */
+int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t nclip, int64_t clip_len,
+                         int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft, int hop,
+                         int win_length, float scale, void* stream);
+
 /* adjoint of se_stft_fwd (autograd of src/evaluate.py:109-120):
  * gspec [rows,F,T,2] (dL/dRe, dL/dIm) -> gx [rows,N]; accumulate != 0 adds into gx. */
 int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop,

@@ -232,6 +232,39 @@ def stitch_ref(segments: torch.Tensor, num_feature: int, stride: int, out_len: i
     return out[..., :out_len]
 
 
+def evaluate_ref(mixture, model, config, stft_models=("mel-rnn", "dcunet", "crn", "dnn", "unet", "rnn-stft-mask"),
+                 monarch=("mel-rnn", "dcunet", "crn", "dnn", "unet", "dccrn", "wav-unet")):
+    """src/evaluate.py:10-98 on CPU (single-source models): z-score, segment (stride = win_length),
+    STFT, model on two half-batches, iSTFT, stitch, de-normalise."""
+    with torch.no_grad():
+        x = mixture
+        if config.dset.norm == "z-score":
+            mean = torch.mean(x, dim=-1, keepdim=True)
+            std = torch.std(x, dim=-1, keepdim=True)
+            x = (x - mean) / (std + 1e-9)
+        stride = config.model.win_length
+        nfeat = int(config.dset.sample_rate * config.model.segment)
+        seg = segment_ref(x, nfeat, stride)
+        nseg, nb, nc, ns = seg.shape
+        batch = seg.reshape(nseg * nb, nc, ns)
+        if config.model.name in stft_models:
+            batch = stft_custom_ref(batch, config.model)
+        if model:
+            half = batch.shape[0] // 2
+            out = torch.cat([model(batch[:half]), model(batch[half:])], 0)
+        else:
+            out = batch
+        if config.model.name in monarch:
+            out = out.unsqueeze(1)
+        if config.model.name in stft_models:
+            out = istft_custom_ref(out, ns, config.model)
+        out = out.reshape(nseg, nb, nc, ns)
+        enhanced = stitch_ref(out, nfeat, stride, mixture.shape[-1])
+        if config.dset.norm == "z-score":
+            enhanced = enhanced * (std + 1e-9) + mean
+    return enhanced
+
+
 def audio_seconds(rows_shape, sample_rate):
     """audio-seconds = clips * N / sample_rate (channels do not multiply)."""
     nbatch, nsample = rows_shape[0], rows_shape[-1]

@@ -216,12 +216,32 @@ int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int 
     if (nsample <= n_fft / 2) return fail(SE_ERR_BAD_ARG, "reflect padding needs nsample > n_fft/2");
     AnaArgs a{};
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
-    a.in = x; a.out = spec; a.in_stride = nsample; a.nsample = (int)nsample; a.in_len = (int)nsample;
+    a.in = x; a.out = spec; a.in_stride = nsample; a.seg_rows = 1; a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
     plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_fwd launch");
+}
+
+int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t nclip, int64_t clip_len, int64_t clip_stride,
+                         int64_t seg_stride, int64_t nsample, int n_fft, int hop, int win_length, float scale, void* stream) {
+    if (!x || !spec) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (nseg <= 0 || nclip <= 0 || clip_len <= 0 || seg_stride <= 0 || clip_stride < clip_len)
+        return fail(SE_ERR_BAD_ARG, "bad segment geometry");
+    const int64_t rows = nseg * nclip;
+    if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
+    if (nsample <= n_fft / 2) return fail(SE_ERR_BAD_ARG, "reflect padding needs nsample > n_fft/2");
+    if ((nseg - 1) * seg_stride >= clip_len) return fail(SE_ERR_BAD_ARG, "last segment starts beyond the clip");
+    AnaArgs a{};
+    if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
+    a.in = x; a.out = spec; a.in_stride = seg_stride; a.clip_stride = clip_stride; a.seg_rows = (int)nclip;
+    a.clip_len = (int)clip_len; a.nsample = (int)nsample; a.in_len = (int)nsample;
+    a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
+    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
+    cudaError_t e;
+    SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_segments_fwd launch");
 }
 
 int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
@@ -267,7 +287,7 @@ int se_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, in
     if (int rc = check_common(rows, length, n_fft, hop, win_length)) return rc;
     AnaArgs a{};
     if (int rc = get_tables(n_fft, hop, win_length, false, scale / (float)n_fft, a.tb)) return rc;
-    a.in = gy; a.out = gspec; a.in_stride = length; a.in_len = (int)length;
+    a.in = gy; a.out = gspec; a.in_stride = length; a.seg_rows = 1; a.in_len = (int)length;
     a.nsample = (int)(n_fft + hop * (nframe - 1)); a.nframe = (int)nframe; a.pad = 0; a.edge_scale = 0.5f;
     plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
     cudaError_t e;
@@ -332,6 +352,7 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
     if (rows <= 0 || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need rows > 0 and nsample >= 2048");
     double* part = reinterpret_cast<double*>(workspace);
     float* refmag = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + loss_partials_bytes(rows, nsample));
+    int nres[3] = {0, 0, 0};
     for (int r = 0; r < 3; ++r) {
         const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
         if (int rc = check_common(rows, nsample, n, hop, win)) return rc;
@@ -343,12 +364,13 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
         cudaError_t e;
         SE_DISPATCH_LOSS_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd launch");
-        e = launch(k_reduce_partials, 1u, 256u, 0, (cudaStream_t)stream, (const double*)part, nctas, sums + 3 * r);
-        if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd reduce launch");
+        nres[r] = nctas;
         part += (size_t)nctas * 3;
         refmag += loss_refmag_floats(rows, nsample, r);
     }
-    return 0;
+    cudaError_t e = launch(k_reduce_partials, 3u, 256u, 0, (cudaStream_t)stream,
+                           (const double*)reinterpret_cast<double*>(workspace), nres[0], nres[1], nres[2], sums);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_fwd reduce launch");
 }
 
 int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsample, float* loss, void* stream) {

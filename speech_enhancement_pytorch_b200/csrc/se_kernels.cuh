@@ -35,7 +35,10 @@ struct AnaArgs {            // analysis: waveform-like -> spectrum
     Tables tb;
     const float* in;        // [rows, in_len]
     float* out;             // spectrum
-    int64_t in_stride;      // floats between rows of `in`
+    int64_t in_stride;      // floats between rows of `in` (segments: between consecutive segments of a clip)
+    int64_t clip_stride;    // segments only: floats between clips; row = seg * seg_rows + clip
+    int seg_rows;           // clips per segment index (1 = plain rows)
+    int clip_len;           // segments only: valid samples per clip (the rest reads as zero); 0 = no limit
     int nsample;            // N (REFLECT / ZEROPAD: valid input samples; ENV: natural padded length)
     int in_len;             // ENV: `length` of gy rows
     int nframe;             // T
@@ -58,12 +61,12 @@ struct SynArgs {            // synthesis: spectrum -> waveform-like
 };
 
 // ------------------------------------------------------------------ padded-signal samplers
-__device__ __forceinline__ float sample_reflect(const float* __restrict__ x, int n_half, int N, int n_fft, int i) {
+__device__ __forceinline__ float sample_reflect(const float* __restrict__ x, int n_half, int N, int n_fft, int i, int nvalid) {
     if (i < 0 || i >= N + n_fft) return 0.f;
     int j = i - n_half;
     j = j < 0 ? -j : j;
     j = j >= N ? 2 * (N - 1) - j : j;
-    return __ldg(x + j);
+    return j < nvalid ? __ldg(x + j) : 0.f;      // nvalid < N: zero-filled tail of the last segments
 }
 
 template <class G>
@@ -85,12 +88,12 @@ __device__ __forceinline__ float inv_env_at(const Tables& tb, int T, int i) {
 // the load held 90 % of the long-scoreboard samples before this change).
 template <class G, int LMODE>
 __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const float* __restrict__ src,
-                                           int p0, const AnaArgs& a, int tid) {
+                                           int p0, const AnaArgs& a, int tid, int nvalid = 0x7fffffff) {
     constexpr int SLOTS = G::SROWS * G::HOP / 2;                 // float2 slots
     constexpr int K = (SLOTS + G::NT - 1) / G::NT;
     float2 v[K];
     const int base = (LMODE == LOAD_ZEROPAD) ? p0 - a.pad : p0 - G::N / 2;   // source index of slot 0
-    const int limit = (LMODE == LOAD_ENV) ? a.in_len : a.nsample;
+    const int limit = (LMODE == LOAD_ENV) ? a.in_len : (a.nsample < nvalid ? a.nsample : nvalid);
     const bool interior = base >= 0 && base + 2 * SLOTS <= limit &&
                           (LMODE != LOAD_ENV || p0 + 2 * SLOTS <= a.nsample);
     if (interior) {                                              // uniform per CTA: plain streaming loads
@@ -115,8 +118,8 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
             if (slot >= SLOTS) continue;
             const int i = p0 + 2 * slot;
             if (LMODE == LOAD_REFLECT) {
-                v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i),
-                                   sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1));
+                v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i, nvalid),
+                                   sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1, nvalid));
             } else if (LMODE == LOAD_ZEROPAD) {
                 const int j = i - a.pad;
                 v[k] = make_float2((j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f,
@@ -337,11 +340,17 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
-    const float* src = a.in + (size_t)row * a.in_stride;
+    const int seg = row / a.seg_rows, clip = row - seg * a.seg_rows;
+    const float* src = a.in + (size_t)seg * a.in_stride + (size_t)clip * a.clip_stride;
+    int nvalid = 0x7fffffff;
+    if (a.clip_len > 0) {
+        const int64_t left = (int64_t)a.clip_len - (int64_t)seg * a.in_stride;
+        nvalid = left < 0 ? 0 : (left < a.nsample ? (int)left : a.nsample);
+    }
     for (int g = 0; g < a.gpc; ++g) {
         const int f_base = (chunk * a.gpc + g) * G::FR;
         if (f_base >= a.nframe) break;
-        fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid);
+        fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid, nvalid);
         __syncthreads();
         analysis_passes<G>(stage, a.tb, zb, unit, fr);
         const int t = f_base + fr;
@@ -561,10 +570,12 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     }
 }
 
-// reduce per-CTA partials -> sums[3] in a fixed order (one CTA, deterministic)
-__global__ void k_reduce_partials(const double* __restrict__ partials, int n, double* __restrict__ sums) {
+// reduce per-CTA partials -> sums[9] in a fixed order (one CTA per resolution, deterministic)
+__global__ void k_reduce_partials(const double* __restrict__ partials, int n0, int n1, int n2, double* __restrict__ sums) {
     __shared__ double sh[3][256];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, r = blockIdx.x;
+    const int n = r == 0 ? n0 : (r == 1 ? n1 : n2);
+    partials += (size_t)3 * (r == 0 ? 0 : (r == 1 ? n0 : n0 + n1));
     double acc[3] = {0.0, 0.0, 0.0};
     for (int i = tid; i < n; i += 256)
         for (int j = 0; j < 3; ++j) acc[j] += partials[(size_t)i * 3 + j];
@@ -575,7 +586,7 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n, do
             for (int j = 0; j < 3; ++j) sh[j][tid] += sh[j][tid + s];
         __syncthreads();
     }
-    if (tid < 3) sums[tid] = sh[tid][0];
+    if (tid < 3) sums[3 * r + tid] = sh[tid][0];
 }
 
 __global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss) {

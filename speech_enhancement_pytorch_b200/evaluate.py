@@ -41,3 +41,101 @@ def istft_custom(tensor, length, config):
         length = hop * (nt - 1)
     wave = ops.istft(tensor.reshape(-1, nf, nt, 2), int(length), n_fft, hop, win, float(win))
     return wave.reshape(*lead, wave.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluate(): the inference-side caller of the path, src/evaluate.py:10-98
+
+MULTI_SPEECH_SEPERATION_MODELS = ("demucs", "conv-tasnet", "rnn-stft-mask")          # src/model/types.py:1
+MONARCH_SPEECH_SEPARTAION_MODELS = ("mel-rnn", "dcunet", "crn", "dnn", "unet", "dccrn", "wav-unet")   # :3
+STFT_MODELS = ("mel-rnn", "dcunet", "crn", "dnn", "unet", "rnn-stft-mask")           # src/model/types.py:5
+
+
+def segment_stft(wave, num_feature, stride, config):
+    """`_prepare_input_wav_zero_filled` (src/evaluate.py:164-183) + reshape (:35-36) + `stft_custom` (:39)
+    in one launch: the overlapping segments are never materialised (they are strided views of the clip;
+    the zero-filled tail is synthesised in the kernel).  wave [B,C,L] -> [nseg*B, C, F, T, 2]."""
+    import torch
+    from . import _native as nv
+    n_fft, hop, win = _cfg(config)
+    ops._check_cfg(n_fft, hop, win)
+    if wave.dim() != 3:
+        raise ValueError("segment_stft expects [B,C,L]")
+    nb, nc, length = wave.shape
+    if length < num_feature:
+        raise AssertionError("the length of data is too short comparing the number of features...")
+    rem = (length - num_feature) % stride
+    padded = length + (stride - rem if rem else 0)
+    nseg = (padded - num_feature) // stride + 1
+    x = ops._as_f32(wave).contiguous()
+    nv.require_cuda_f32(x)
+    nf, nt = n_fft // 2 + 1, 1 + num_feature // hop
+    out = torch.empty((nseg * nb, nc, nf, nt, 2), dtype=torch.float32, device=x.device)
+    with nv.on_device(x.device):
+        nv.check(nv.lib().se_stft_segments_fwd(x.data_ptr(), out.data_ptr(), nseg, nb * nc, length, length, stride,
+                                               num_feature, n_fft, hop, win, 1.0 / win, nv.stream_ptr(x.device)))
+    return out, nseg
+
+
+def stitch_segments(output, num_feature, stride, out_len):
+    """src/evaluate.py:84-90 without the Python loop: the first segment whole, then the last `stride`
+    samples of every later segment.  output [nseg, ..., num_feature] -> [..., out_len]."""
+    import torch
+    nseg = output.shape[0]
+    head = output[0]
+    if nseg == 1:
+        return head[..., :out_len]
+    tails = output[1:, ..., num_feature - stride:]                       # [nseg-1, ..., stride]
+    tails = tails.movedim(0, -2).reshape(*output.shape[1:-1], (nseg - 1) * stride)
+    return torch.cat([head, tails], dim=-1)[..., :out_len]
+
+
+def evaluate(mixture, model, device, config):
+    """Drop-in for `evaluate(mixture, model, device, config)` (src/evaluate.py:10-98): normalise,
+    cut into `config.model.segment`-second segments with stride win_length, STFT, model, iSTFT,
+    stitch, de-normalise.  Everything runs on `device` (the reference runs the STFT on the CPU tensor
+    and moves to the device afterwards, :39,50)."""
+    import torch
+    with torch.no_grad():
+        x = mixture.to(device)
+        norm = getattr(config.dset, "norm", None)
+        if norm == "z-score":
+            mean = torch.mean(x, dim=-1, keepdim=True)
+            std = torch.std(x, dim=-1, keepdim=True)
+            x = (x - mean) / (std + 1e-9)
+        elif norm == "linear-scale":
+            # the reference indexes the (values, indices) tuple of torch.max here and fails (:23-25)
+            raise NotImplementedError("dset.norm='linear-scale' is broken in the reference (src/evaluate.py:23-25)")
+        stride = config.model.win_length
+        num_feature = int(config.dset.sample_rate * config.model.segment)
+        nbatch, nchannel, length = x.shape
+        name = config.model.name
+        if name in STFT_MODELS:
+            batch, nseg = segment_stft(x, num_feature, stride, config.model)
+        else:
+            rem = (length - num_feature) % stride
+            xp = torch.nn.functional.pad(x, [0, stride - rem]) if rem else x
+            batch = xp.unfold(-1, num_feature, stride).movedim(-2, 0)             # [nseg,B,C,N] view
+            nseg = batch.shape[0]
+            batch = batch.reshape(nseg * nbatch, nchannel, num_feature)
+        if model:
+            model.eval()
+            half = int(batch.shape[0] // 2)                                      # :48-56 two half-batches
+            output = torch.cat([model(batch[:half]), model(batch[half:])], dim=0)
+        else:
+            output = batch
+        if name in MONARCH_SPEECH_SEPARTAION_MODELS:
+            output = torch.unsqueeze(output, dim=1)
+        if name in STFT_MODELS:
+            output = istft_custom(output, num_feature, config.model)
+        if model and name in MULTI_SPEECH_SEPERATION_MODELS:
+            nsrc = len(config.model.sources)
+            output = output.reshape(nseg, nbatch, nsrc, nchannel, num_feature)
+        else:
+            output = output.reshape(nseg, nbatch, nchannel, num_feature)
+        enhanced = stitch_segments(output, num_feature, stride, length)
+        if norm == "z-score":
+            if enhanced.dim() == mean.dim() + 1:
+                mean, std = mean.unsqueeze(1), std.unsqueeze(1)
+            enhanced = enhanced * (std + 1e-9) + mean
+    return enhanced

@@ -168,3 +168,12 @@ def enhance_bwd(gy, x, mask, n, hop, win, mode, pre_tanh):
     check(lib().se_enhance_bwd(ptr(gy), ptr(x), ptr(mask), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win),
                                ci(mode), ci(int(pre_tanh)), None))
     return out
+
+
+def stft_segments_fwd(x, nseg, seg_stride, nsample, n, hop, win, scale):
+    nclip, clip_len = x.shape
+    T = 1 + nsample // hop
+    out = np.full((nseg * nclip, n // 2 + 1, T, 2), np.nan, np.float32)
+    check(lib().se_stft_segments_fwd(ptr(x), ptr(out), i64(nseg), i64(nclip), i64(clip_len), i64(clip_len),
+                                     i64(seg_stride), i64(nsample), ci(n), ci(hop), ci(win), f32(scale), None))
+    return out

@@ -179,3 +179,15 @@ def test_emu_fused_enhance(n, hop, win, N, mode, name):
         (gm_ref,) = torch.autograd.grad(yr, mt, torch.from_numpy(gy)[:, None].double())
         gm = E.enhance_bwd(gy, x, m, n, hop, win, mode, pre_tanh)
         assert rel(gm, gm_ref.numpy()[:, 0]) < 2e-6
+
+
+def test_emu_segment_stft_matches_reference_segmenting():
+    """evaluate()'s zero-filled overlapping segments + STFT in one launch (src/evaluate.py:29-39,164-183)."""
+    g = golden("segments")
+    nfeat, stride = (int(v) for v in g["meta"])
+    wav = np.ascontiguousarray(g["wav"][0])                       # [C, L]
+    nseg = g["seg"].shape[0]
+    got = E.stft_segments_fwd(wav, nseg, stride, nfeat, 512, 128, 512, 1.0 / 512)
+    cfg = oref.make_config(512, 128, 512)
+    want = oref.stft_custom_ref(torch.from_numpy(g["seg"]).reshape(nseg, wav.shape[0], nfeat), cfg).numpy()
+    assert rel(got.reshape(want.shape), want) < 1e-6

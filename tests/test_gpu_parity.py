@@ -325,3 +325,34 @@ def test_fused_chain_full_size_cfg2(se):
     y1 = se.enhance(x, raw, c, "E", True)
     y2 = se.istft_custom(se.apply_mask(se.stft_custom(x, c), raw, "E", True), 64000, c)
     assert float((y1 - y2).abs().max()) < 1e-5 * float(y2.abs().max())
+
+
+@pytest.mark.parametrize("name,model", [("dnn", None), ("dnn", "mask"), ("demucs", None)])
+def test_evaluate_matches_reference_flow(se, oref, name, model):
+    """evaluate(): z-score, segment (stride = win_length), STFT, model, iSTFT, stitch (src/evaluate.py:10-98)."""
+    g = torch.Generator().manual_seed(21)
+    mix = torch.randn(1, 2, 30000, generator=g) * 0.3 + 0.05
+    config = types.SimpleNamespace(
+        dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
+        model=types.SimpleNamespace(name=name, segment=0.512, n_fft=512, hop_length=128, win_length=512, center=True))
+    fn = None
+    if model:
+        class Toy(torch.nn.Module):                      # a spectrogram "model": fixed smooth real mask
+            def forward(self, spec):
+                f = torch.linspace(0.2, 1.0, spec.shape[-3], device=spec.device)[:, None, None]
+                return spec * f
+        fn = Toy()
+    want = oref.evaluate_ref(mix, fn, config)
+    got = se.evaluate(mix, fn.cuda() if fn else None, "cuda", config)
+    assert got.shape == want.shape
+    assert rel(got, want) < TOL_SPEC
+
+
+def test_evaluate_identity_property_like_reference_test(se):
+    """test/test_eval.py:5-40: evaluate with no model is the identity (error_rate 1e-10 there, fp32 here)."""
+    mix = torch.randn(1, 1, 16000 * 3, device="cuda")
+    config = types.SimpleNamespace(
+        dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
+        model=types.SimpleNamespace(name="dnn", segment=1.024, n_fft=512, hop_length=128, win_length=512, center=True))
+    out = se.evaluate(mix, None, "cuda", config)
+    assert float((out - mix).abs().max()) < 1e-5
