@@ -29,8 +29,15 @@ EXPORTS = (
 MASK_MODES = {"real": 0, "E": 1, "C": 2, "R": 3}
 
 
+BUILD_DIR = os.path.join(_PKG, "build")
+
+
 def _sources():
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f)))
+
+
+def _units():
+    return [p for p in _sources() if p.endswith(".cu")]
 
 
 def needs_build() -> bool:
@@ -42,17 +49,33 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/se_capi.cu for sm_100a with nvcc into the in-tree libse_b200.so."""
+    """Compile csrc/*.cu for sm_100a with nvcc (one process per translation unit, in parallel) and
+    link the in-tree libse_b200.so."""
     if not (force or needs_build()):
         return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH, os.path.join(CSRC, "se_capi.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
+        res = subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, res
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, _units()))
+    log = ""
+    for obj, res in results:
+        log += res.stderr
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB_PATH] + [o for o, _ in results], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        with open(os.path.join(BUILD_DIR, "ptxas.log"), "w") as f:
+            f.write(log)
     return LIB_PATH
 
 

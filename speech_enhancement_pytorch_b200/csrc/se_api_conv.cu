@@ -1,56 +1,8 @@
-// included at the end of se_capi.cu (namespace se is in scope via `using`)
+// se_api_conv.cu -- DCCRN ConvSTFT / ConviSTFT entry points.
+#include "se_host.h"
+#include "se_conv.cuh"
 
-extern "C" int se_enhance_fwd(const float* x, const float* mask, float* y, int64_t rows, int64_t nsample, int n_fft, int hop,
-                   int win_length, int mode, int pre_tanh, void* stream) {
-    if (!x || !mask || !y) return fail(SE_ERR_BAD_ARG, "null pointer");
-    if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
-    if (mode < 0 || mode > 3) return fail(SE_ERR_UNSUPPORTED, "mask mode must be REAL/E/C/R");
-    if (nsample <= n_fft / 2) return fail(SE_ERR_BAD_ARG, "reflect padding needs nsample > n_fft/2");
-    const int64_t T = 1 + nsample / hop;
-    if (!envelope_ok(n_fft, hop, win_length, false, T, n_fft / 2, n_fft / 2 + nsample, 1e-11))
-        return fail(SE_ERR_ENVELOPE, "window overlap add min < 1e-11 (torch.istft raises the same)");
-    EnhArgs a{};
-    if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f / (float)win_length, a.ta)) return rc;
-    if (int rc = get_tables(n_fft, hop, win_length, false, (float)win_length / (float)n_fft, a.ts)) return rc;
-    a.x = x; a.mask = mask; a.out = y; a.nsample = (int)nsample; a.nframe = (int)T;
-    a.b_lo = (n_fft / 2) / hop; a.b_hi = (int)((n_fft / 2 + nsample + hop - 1) / hop);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop);
-    a.mode = mode; a.pre_tanh = pre_tanh;
-    cudaError_t e;
-    SE_DISPATCH_MASK(mode, pre_tanh, SE_DISPATCH_GEO(n_fft, hop, (e = launch(k_enhance_fwd<G, MODE, TANH>,
-        (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ISTFT, (cudaStream_t)stream, a))));
-    return e == cudaSuccess ? 0 : cuda_fail(e, "se_enhance_fwd launch");
-}
-
-template <class G>
-static cudaError_t run_enhance_bwd(const EnhArgs& a, int64_t rows, cudaStream_t st) {
-    cudaError_t e;
-    SE_DISPATCH_MASK(a.mode, a.pre_tanh, (e = launch(k_enhance_bwd<G, MODE, TANH>, (unsigned)(rows * a.nchunks), G::NT,
-                                                     2 * Smem<G>::ZB + Smem<G>::STAGE, st, a)));
-    return e;
-}
-
-extern "C" int se_enhance_bwd(const float* gy, const float* x, const float* mask, float* gmask, int64_t rows, int64_t nsample,
-                   int n_fft, int hop, int win_length, int mode, int pre_tanh, void* stream) {
-    if (!gy || !x || !mask || !gmask) return fail(SE_ERR_BAD_ARG, "null pointer");
-    if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
-    if (mode < 0 || mode > 3) return fail(SE_ERR_UNSUPPORTED, "mask mode must be REAL/E/C/R");
-    if (n_fft > 1024) return fail(SE_ERR_UNSUPPORTED, "se_enhance_bwd keeps two transforms in shared memory: n_fft <= 1024 "
-                                                      "(compose se_stft_fwd + se_istft_bwd + se_mask_bwd for 2048)");
-    const int64_t T = 1 + nsample / hop;
-    EnhArgs a{};
-    if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f / (float)win_length, a.ta)) return rc;
-    if (int rc = get_tables(n_fft, hop, win_length, false, (float)win_length / (float)n_fft, a.ts)) return rc;
-    a.x = x; a.mask = mask; a.gy = gy; a.out = gmask; a.nsample = (int)nsample; a.nframe = (int)T;
-    plan_analysis(rows, T, a.gpc, a.nchunks);
-    a.mode = mode; a.pre_tanh = pre_tanh;
-    cudaError_t e;
-    if (n_fft == 512 && hop == 128) e = run_enhance_bwd<Geo<512, 128, 256>>(a, rows, (cudaStream_t)stream);
-    else if (n_fft == 512) e = run_enhance_bwd<Geo<512, 256, 256>>(a, rows, (cudaStream_t)stream);
-    else if (hop == 256) e = run_enhance_bwd<Geo<1024, 256, 256>>(a, rows, (cudaStream_t)stream);
-    else e = run_enhance_bwd<Geo<1024, 512, 256>>(a, rows, (cudaStream_t)stream);
-    return e == cudaSuccess ? 0 : cuda_fail(e, "se_enhance_bwd launch");
-}
+using namespace se;
 
 extern "C" int se_conv_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int win_len, int win_inc, int fft_len,
                      void* stream) {

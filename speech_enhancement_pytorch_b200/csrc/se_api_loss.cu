@@ -1,0 +1,113 @@
+// se_api_loss.cu -- multi-resolution STFT loss entry points.
+#include "se_host.h"
+
+using namespace se;
+
+static const int kRes[3][3] = {{512, 128, 512}, {1024, 256, 1024}, {2048, 512, 2048}};
+
+#define SE_DISPATCH_LOSS_GEO(n_fft, CALL)                                              \
+    do {                                                                               \
+        if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                      \
+        else if (n_fft == 1024) { using G = Geo<1024, 256, 512>; CALL; }               \
+        else { using G = Geo<2048, 512, 512>; CALL; }                                  \
+    } while (0)
+
+template <class G>
+static cudaError_t run_loss_fwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
+    return launch(k_loss_fwd<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, st, a);
+}
+template <class G>
+static cudaError_t run_loss_bwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
+    return launch(k_loss_bwd<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ADJ, st, a);
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------- MR-STFT loss
+static int loss_fwd_plan(int64_t rows, int64_t nsample, int r, int& gpc, int& nchunks) {
+    const int64_t T = 1 + nsample / kRes[r][1];
+    plan_analysis(rows, T, gpc, nchunks);
+    return (int)(rows * nchunks);
+}
+
+// workspace layout: [per-CTA partial sums (double) for the 3 resolutions | |B| per resolution (float)]
+static int64_t loss_partials_bytes(int64_t rows, int64_t nsample) {
+    int64_t total = 0;
+    for (int r = 0; r < 3; ++r) {
+        int gpc, nchunks;
+        total += (int64_t)loss_fwd_plan(rows, nsample, r, gpc, nchunks) * 3 * sizeof(double);
+    }
+    return (total + 255) / 256 * 256;
+}
+static int64_t loss_refmag_floats(int64_t rows, int64_t nsample, int r) {
+    return rows * (kRes[r][0] / 2 + 1) * (1 + nsample / kRes[r][1]);
+}
+
+int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample) {
+    int64_t total = loss_partials_bytes(rows, nsample);
+    for (int r = 0; r < 3; ++r) total += loss_refmag_floats(rows, nsample, r) * (int64_t)sizeof(float);
+    return total;
+}
+
+int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums,
+                       void* workspace, void* stream) {
+    if (!est || !ref || !sums || !workspace) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (rows <= 0 || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need rows > 0 and nsample >= 2048");
+    double* part = reinterpret_cast<double*>(workspace);
+    float* refmag = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + loss_partials_bytes(rows, nsample));
+    int nres[3] = {0, 0, 0};
+    for (int r = 0; r < 3; ++r) {
+        const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
+        if (int rc = check_common(rows, nsample, n, hop, win)) return rc;
+        LossArgs a{};
+        if (int rc = get_tables(n, hop, win, false, 0.5f, a.tb)) return rc;
+        a.est = est; a.ref = ref; a.partials = part; a.refmag = refmag;
+        a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
+        const int nctas = loss_fwd_plan(rows, nsample, r, a.gpc, a.nchunks);
+        cudaError_t e;
+        SE_DISPATCH_LOSS_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
+        if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd launch");
+        nres[r] = nctas;
+        part += (size_t)nctas * 3;
+        refmag += loss_refmag_floats(rows, nsample, r);
+    }
+    cudaError_t e = launch(k_reduce_partials, 3u, 256u, 0, (cudaStream_t)stream,
+                           (const double*)reinterpret_cast<double*>(workspace), nres[0], nres[1], nres[2], sums);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_fwd reduce launch");
+}
+
+int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsample, float* loss, void* stream) {
+    if (!sums || !loss || global_rows <= 0) return fail(SE_ERR_BAD_ARG, "null pointer or empty batch");
+    double cnt[3];
+    for (int r = 0; r < 3; ++r)
+        cnt[r] = (double)global_rows * (kRes[r][0] / 2 + 1) * (double)(1 + nsample / kRes[r][1]);
+    cudaError_t e = launch(k_loss_value, 1u, 32u, 0, (cudaStream_t)stream, sums, cnt[0], cnt[1], cnt[2], loss);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_value launch");
+}
+
+int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* sums, const float* gout, int64_t global_rows,
+                       int64_t rows, int64_t nsample, float* g_est, void* stream) {
+    if (!est || !workspace || !sums || !gout || !g_est) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (rows <= 0 || global_rows < rows || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need 0 < rows <= global_rows, nsample >= 2048");
+    const float* refmag = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + loss_partials_bytes(rows, nsample));
+    for (int r = 0; r < 3; ++r) {
+        const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
+        if (int rc = check_common(rows, nsample, n, hop, win)) return rc;
+        LossArgs a{};
+        if (int rc = get_tables(n, hop, win, false, 0.5f, a.tb)) return rc;
+        a.est = est; a.refmag = const_cast<float*>(refmag); a.g_est = g_est; a.sums = sums + 3 * r; a.gout = gout;
+        a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
+        a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
+        a.nchunks = (a.b_hi + 12) / 13;          // single-group chunks: 16 - (OLA-1) blocks each, no carry
+        a.accumulate = r > 0;
+        a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
+        a.inv_res = 1.0f / 3.0f;
+        cudaError_t e;
+        SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd<G>(a, rows, (cudaStream_t)stream)));
+        if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_bwd launch");
+        refmag += loss_refmag_floats(rows, nsample, r);
+    }
+    return 0;
+}
+
+}  // extern "C"

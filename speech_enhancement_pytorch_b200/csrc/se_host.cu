@@ -1,0 +1,149 @@
+// se_host.cu -- constant-table cache, launch planning, error string (shared by every se_api_*.cu).
+#include "se_host.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+namespace se {
+
+static thread_local std::string g_err;
+const char* last_error() { return g_err.c_str(); }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(SE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// ------------------------------------------------------------------ constant tables
+struct TableKey {
+    int dev, n, hop, win_len, front;
+    uint32_t scale_bits;
+    bool operator<(const TableKey& o) const {
+        return std::tie(dev, n, hop, win_len, front, scale_bits) <
+               std::tie(o.dev, o.n, o.hop, o.win_len, o.front, o.scale_bits);
+    }
+};
+static std::mutex g_mu;
+static std::map<TableKey, Tables> g_tables;
+
+static void host_window(int n, int win_len, bool front, std::vector<double>& w) {
+    w.assign(n, 0.0);
+    const int left = front ? 0 : (n - win_len) / 2;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int j = 0; j < win_len; ++j) w[left + j] = 0.5 - 0.5 * std::cos(two_pi * j / win_len);
+}
+
+// `scale` multiplies the window; front=true puts a short window at the start of the frame (DCCRN)
+int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    TableKey key{dev, n, hop, win_len, front ? 1 : 0, 0};
+    std::memcpy(&key.scale_bits, &scale, 4);
+    std::lock_guard<std::mutex> lock(g_mu);
+    auto it = g_tables.find(key);
+    if (it != g_tables.end()) { out = it->second; return 0; }
+    const int M = n / 2;
+    const double two_pi = 6.283185307179586476925286766559;
+    std::vector<double> w;
+    host_window(n, win_len, front, w);
+    std::vector<float> win(n), w2(n), inv_env(hop);
+    std::vector<float2> tw(M), twn(M);
+    for (int j = 0; j < n; ++j) {
+        win[j] = (float)(w[j] * (double)scale);
+        const float wf = (float)w[j];
+        w2[j] = wf * wf;
+    }
+    for (int k = 0; k < M; ++k) {
+        tw[k] = make_float2((float)std::cos(two_pi * k / M), (float)-std::sin(two_pi * k / M));
+        twn[k] = make_float2((float)std::cos(two_pi * k / n), (float)-std::sin(two_pi * k / n));
+    }
+    for (int o = 0; o < hop; ++o) {
+        float e = 0.f;
+        for (int q = 0; o + q * hop < n; ++q) e += w2[o + q * hop];
+        inv_env[o] = e > 0.f ? 1.0f / e : 0.f;
+    }
+    float *d_win = nullptr, *d_w2 = nullptr, *d_env = nullptr;
+    float2 *d_tw = nullptr, *d_twn = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&d_win, n * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&d_w2, n * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&d_env, hop * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&d_tw, M * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&d_twn, M * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaMemcpy(d_win, win.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_w2, w2.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_env, inv_env.data(), hop * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tw, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(d_twn, twn.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tables)");
+    out = Tables{d_win, d_tw, d_twn, d_w2, d_env};
+    g_tables[key] = out;
+    return 0;
+}
+
+// torch.istft's "window overlap add min" check, evaluated on the host (no device sync):
+// the envelope depends only on the configuration.
+bool envelope_ok(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_) {
+    std::vector<double> w;
+    host_window(n, win_len, front, w);
+    const int ola = (n + hop - 1) / hop;
+    // blocks whose set of contributing frames is not "all": first ola-1 and those past T-1
+    auto env_at = [&](int64_t i) {
+        const int64_t b = i / hop;
+        const int o = (int)(i - b * hop);
+        double e = 0.0;
+        for (int q = 0; q < ola && o + q * hop < n; ++q) {
+            const int64_t t = b - q;
+            if (t >= 0 && t < T) { const float wf = (float)w[o + q * hop]; e += (double)(wf * wf); }
+        }
+        return e;
+    };
+    const int64_t natural = n + hop * (T - 1);
+    hi = hi < natural ? hi : natural;
+    if (hi <= lo) return true;
+    const int64_t edge = (int64_t)ola * hop;
+    for (int64_t i = lo; i < hi; ++i) {
+        if (i >= lo + edge + hop && i < hi - edge - hop) { i = hi - edge - hop - 1; continue; }   // interior is periodic
+        if (std::fabs(env_at(i)) < floor_) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------ launch planning
+static int g_target_ctas = 148 * 8;
+
+void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks) {
+    const int64_t ng = (T + 15) / 16;
+    int64_t g = (rows * ng) / g_target_ctas;
+    g = g < 1 ? 1 : (g > 8 ? 8 : g);
+    gpc = (int)g;
+    nchunks = (int)((ng + g - 1) / g);
+}
+int plan_synthesis(int64_t rows, int nb, int ola) {
+    int64_t ng = (nb + 15) / 16;
+    int64_t g = (rows * ng) / g_target_ctas;
+    g = g < 1 ? 1 : (g > 8 ? 8 : g);
+    const int cb_max = (int)(16 * g) - (ola - 1);
+    int nchunks = (nb + cb_max - 1) / cb_max;
+    return nchunks < 1 ? 1 : nchunks;
+}
+
+int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length) {
+    if (rows <= 0 || nsample <= 0) return fail(SE_ERR_BAD_ARG, "rows and nsample must be positive");
+    if (n_fft != 512 && n_fft != 1024 && n_fft != 2048)
+        return fail(SE_ERR_UNSUPPORTED, "n_fft must be 512, 1024 or 2048 (no fallback path exists)");
+    if (hop * 4 != n_fft && hop * 2 != n_fft)
+        return fail(SE_ERR_UNSUPPORTED, "hop_length must be n_fft/4 or n_fft/2");
+    if (win_length < 2 || win_length > n_fft) return fail(SE_ERR_UNSUPPORTED, "need 2 <= win_length <= n_fft");
+    if (rows * ((nsample / hop + 1 + 15) / 16) > 0x7fffffffLL) return fail(SE_ERR_BAD_ARG, "problem too large for one launch");
+    return 0;
+}
+
+}  // namespace se
+
+extern "C" int se_version(void) { return 100; }
+extern "C" const char* se_last_error(void) { return se::last_error(); }

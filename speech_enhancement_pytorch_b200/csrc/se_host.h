@@ -1,0 +1,47 @@
+// se_host.h -- host-side helpers shared by the C-ABI translation units (se_api_*.cu).
+#pragma once
+#include "../../include/se_b200.h"
+#include "se_kernels.cuh"
+
+#include <string>
+
+namespace se {
+
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+const char* last_error();
+// constant tables per (device, n, hop, win_len, placement, scale); `scale` multiplies the window,
+// front=true puts a short window at the start of the frame (DCCRN)
+int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out);
+// torch.istft's "window overlap add min" check on the host (no device sync)
+bool envelope_ok(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_);
+void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks);
+int plan_synthesis(int64_t rows, int nb, int ola);
+int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length);
+
+// MODE (0..3) x TANH -> compile-time template arguments
+#define SE_DISPATCH_MASK(mode, pre_tanh, CALL)                                         \
+    do {                                                                               \
+        if (pre_tanh) {                                                                \
+            constexpr bool TANH = true;                                                \
+            if (mode == 0) { constexpr int MODE = 0; CALL; } else if (mode == 1) { constexpr int MODE = 1; CALL; } \
+            else if (mode == 2) { constexpr int MODE = 2; CALL; } else { constexpr int MODE = 3; CALL; }           \
+        } else {                                                                       \
+            constexpr bool TANH = false;                                               \
+            if (mode == 0) { constexpr int MODE = 0; CALL; } else if (mode == 1) { constexpr int MODE = 1; CALL; } \
+            else if (mode == 2) { constexpr int MODE = 2; CALL; } else { constexpr int MODE = 3; CALL; }           \
+        }                                                                              \
+    } while (0)
+
+#define SE_DISPATCH_GEO(n_fft, hop, CALL)                                              \
+    do {                                                                               \
+        if (n_fft == 512 && hop == 128) { using G = Geo<512, 128, 256>; CALL; }        \
+        else if (n_fft == 512 && hop == 256) { using G = Geo<512, 256, 256>; CALL; }   \
+        else if (n_fft == 1024 && hop == 256) { using G = Geo<1024, 256, 256>; CALL; } \
+        else if (n_fft == 1024 && hop == 512) { using G = Geo<1024, 512, 256>; CALL; } \
+        else if (n_fft == 2048 && hop == 512) { using G = Geo<2048, 512, 512>; CALL; } \
+        else { using G = Geo<2048, 1024, 512>; CALL; }                                 \
+    } while (0)
+
+
+}  // namespace se

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
 }
 
 // reduce per-CTA partials -> sums[9] in a fixed order (one CTA per resolution, deterministic)
-__global__ void k_reduce_partials(const double* __restrict__ partials, int n0, int n1, int n2, double* __restrict__ sums) {
+static __global__ void k_reduce_partials(const double* __restrict__ partials, int n0, int n1, int n2, double* __restrict__ sums) {
     __shared__ double sh[3][256];
     const int tid = threadIdx.x, r = blockIdx.x;
     const int n = r == 0 ? n0 : (r == 1 ? n1 : n2);
@@ -589,7 +589,7 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int n0, i
     if (tid < 3) sums[3 * r + tid] = sh[tid][0];
 }
 
-__global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss) {
+static __global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const double cnt[3] = {c0, c1, c2};
         double total = 0.0;

@@ -16,11 +16,15 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libse_b200_emu.so")
 
 
+def _units():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))] + [
         os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"),
         os.path.join(ROOT, "include", "se_b200.h")]
     return any(os.path.getmtime(s) > t for s in srcs)
@@ -29,11 +33,18 @@ def _stale():
 def build(force=False):
     if not (force or _stale()):
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(BUILD, exist_ok=True)
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-DSE_EMULATE", "-x", "c++", os.path.join(CSRC, "se_capi.cu"),
-           "-x", "c++", os.path.join(HERE, "cuda_emu.cpp"), "-I", HERE, "-I", CSRC,
-           "-shared", "-fPIC", "-o", LIB]
-    subprocess.run(cmd, check=True)
+    flags = ["-O1", "-g", "-std=c++17", "-DSE_EMULATE", "-fPIC", "-I", HERE, "-I", CSRC]
+
+    def one(src):
+        obj = os.path.join(BUILD, os.path.basename(src) + ".o")
+        subprocess.run(["g++"] + flags + ["-x", "c++", "-c", src, "-o", obj], check=True)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        objs = list(pool.map(one, _units() + [os.path.join(HERE, "cuda_emu.cpp")]))
+    subprocess.run(["g++", "-shared", "-o", LIB] + objs, check=True)
     return LIB
 
 
