@@ -260,18 +260,44 @@ __device__ __forceinline__ Chunk make_chunk(int chunk, int nchunks, int b_lo, in
 
 // ------------------------------------------------------------------ emitters
 template <class G>
+__device__ __forceinline__ void emit_istft_one(const float* __restrict__ ostage, float* __restrict__ y_row,
+                                               int blk, int o, int b, const SynArgs& a) {
+    const int i = b * G::HOP + o;
+    const int s = i - G::N / 2;
+    if (s < 0 || s >= a.out_len) return;
+    float r = 0.f;
+    if (i < a.nsample) r = ostage[blk * G::SROW + o] * inv_env_at<G>(a.tb, a.nframe, i);
+    y_row[s] = r;
+}
+
+template <class G>
 __device__ __forceinline__ void emit_istft(const float* __restrict__ ostage, float* __restrict__ y_row,
                                            int f_base, const Chunk& c, const SynArgs& a, int tid) {
-    for (int idx = tid; idx < G::FR * G::HOP; idx += G::NT) {
-        const int blk = idx / G::HOP, o = idx - blk * G::HOP;
-        const int b = f_base + blk;
-        if (b < c.b0 || b >= c.b1) continue;
-        const int i = b * G::HOP + o;
-        const int s = i - G::N / 2;
-        if (s < 0 || s >= a.out_len) continue;
-        float r = 0.f;
-        if (i < a.nsample) r = ostage[blk * G::SROW + o] * inv_env_at<G>(a.tb, a.nframe, i);
-        y_row[s] = r;
+    if ((reinterpret_cast<uintptr_t>(y_row) & 15) == 0 && (G::HOP & 3) == 0) {
+        // 128-bit stores: 4 consecutive samples never straddle a hop block, and s = i - n/2 keeps 4-alignment
+        for (int idx = tid; idx < G::FR * G::HOP / 4; idx += G::NT) {
+            const int e = 4 * idx;
+            const int blk = e / G::HOP, o = e - blk * G::HOP;
+            const int b = f_base + blk;
+            if (b < c.b0 || b >= c.b1) continue;
+            const int i = b * G::HOP + o, s = i - G::N / 2;
+            if (s >= 0 && s + 3 < a.out_len && i + 3 < a.nsample && b >= G::OLA - 1 && b <= a.nframe - 1) {
+                const float2 v0 = *reinterpret_cast<const float2*>(ostage + blk * G::SROW + o);
+                const float2 v1 = *reinterpret_cast<const float2*>(ostage + blk * G::SROW + o + 2);
+                const float4 w = __ldg(reinterpret_cast<const float4*>(a.tb.inv_env + o));
+                *reinterpret_cast<float4*>(y_row + s) = make_float4(v0.x * w.x, v0.y * w.y, v1.x * w.z, v1.y * w.w);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) emit_istft_one<G>(ostage, y_row, blk, o + k, b, a);
+            }
+        }
+    } else {
+        for (int idx = tid; idx < G::FR * G::HOP; idx += G::NT) {
+            const int blk = idx / G::HOP, o = idx - blk * G::HOP;
+            const int b = f_base + blk;
+            if (b < c.b0 || b >= c.b1) continue;
+            emit_istft_one<G>(ostage, y_row, blk, o, b, a);
+        }
     }
 }
 
@@ -691,11 +717,31 @@ struct MaskMath {
     }
 };
 
+// Two bins per thread per iteration with 128-bit accesses (count is even for every supported
+// spectrum shape except odd F*T, handled by the scalar tail).
 template <int MODE, bool TANH>
 __global__ void __launch_bounds__(256) k_mask_fwd_t(const float2* __restrict__ spec, const float* __restrict__ mask,
                                                     float2* __restrict__ out, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(spec) | reinterpret_cast<uintptr_t>(mask) |
+                       reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t pairs = vec ? count / 2 : 0;
+    for (int64_t i = tid0; i < pairs; i += stride) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(spec) + i);
+        float2 m0, m1;
+        if (MODE == 0) {
+            const float2 m = __ldg(reinterpret_cast<const float2*>(mask) + i);
+            m0 = make_float2(m.x, 0.f); m1 = make_float2(m.y, 0.f);
+        } else {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + i);
+            m0 = make_float2(m.x, m.y); m1 = make_float2(m.z, m.w);
+        }
+        const float2 y0 = MaskMath::apply<MODE, TANH>(make_float2(x.x, x.y), m0);
+        const float2 y1 = MaskMath::apply<MODE, TANH>(make_float2(x.z, x.w), m1);
+        reinterpret_cast<float4*>(out)[i] = make_float4(y0.x, y0.y, y1.x, y1.y);
+    }
+    for (int64_t i = 2 * pairs + tid0; i < count; i += stride) {
         const float2 x = __ldg(spec + i);
         const float2 m = MODE == 0 ? make_float2(__ldg(mask + i), 0.f) : __ldg(reinterpret_cast<const float2*>(mask) + i);
         out[i] = MaskMath::apply<MODE, TANH>(x, m);
@@ -707,7 +753,29 @@ __global__ void __launch_bounds__(256) k_mask_bwd_t(const float2* __restrict__ s
                                                     const float2* __restrict__ gout, float* __restrict__ gmask,
                                                     float2* __restrict__ gspec, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(spec) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(gout) |
+                       reinterpret_cast<uintptr_t>(gmask) | reinterpret_cast<uintptr_t>(gspec)) & 15) == 0;
+    const int64_t pairs = vec ? count / 2 : 0;
+    for (int64_t i = tid0; i < pairs; i += stride) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(spec) + i);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gout) + i);
+        float2 m0, m1;
+        if (MODE == 0) {
+            const float2 m = __ldg(reinterpret_cast<const float2*>(mask) + i);
+            m0 = make_float2(m.x, 0.f); m1 = make_float2(m.y, 0.f);
+        } else {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + i);
+            m0 = make_float2(m.x, m.y); m1 = make_float2(m.z, m.w);
+        }
+        float2 gm0, gx0, gm1, gx1;
+        MaskMath::grad<MODE, TANH>(make_float2(x.x, x.y), m0, make_float2(g.x, g.y), gm0, gx0);
+        MaskMath::grad<MODE, TANH>(make_float2(x.z, x.w), m1, make_float2(g.z, g.w), gm1, gx1);
+        if (MODE == 0) reinterpret_cast<float2*>(gmask)[i] = make_float2(gm0.x, gm1.x);
+        else reinterpret_cast<float4*>(gmask)[i] = make_float4(gm0.x, gm0.y, gm1.x, gm1.y);
+        if (gspec) reinterpret_cast<float4*>(gspec)[i] = make_float4(gx0.x, gx0.y, gx1.x, gx1.y);
+    }
+    for (int64_t i = 2 * pairs + tid0; i < count; i += stride) {
         const float2 x = __ldg(spec + i), gy = __ldg(gout + i);
         const float2 m = MODE == 0 ? make_float2(__ldg(mask + i), 0.f) : __ldg(reinterpret_cast<const float2*>(mask) + i);
         float2 gm, gx;
