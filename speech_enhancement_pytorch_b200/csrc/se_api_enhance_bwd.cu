@@ -8,7 +8,7 @@ template <class G>
 static cudaError_t run_enhance_bwd(const EnhArgs& a, int64_t rows, cudaStream_t st) {
     cudaError_t e;
     SE_DISPATCH_MASK(a.mode, a.pre_tanh, (e = launch(k_enhance_bwd<G, MODE, TANH>, (unsigned)(rows * a.nchunks), G::NT,
-                                                     2 * Smem<G>::ZB + Smem<G>::STAGE, st, a)));
+                                                     2 * Smem<G>::ZB + Smem<G>::STAGE + Smem<G>::TABLES + Smem<G>::WINDOW, st, a)));
     return e;
 }
 

@@ -27,10 +27,10 @@ template <class G> struct ConvGeo {
     static constexpr int NOV = 4;                       // ceil(win_len / hop) supported: <= 4
     static constexpr int FROW = G::N + 2 + ((34 - (G::N + 2) % 32) % 32);   // frame row stride == 2 mod 32
     static constexpr int RING = G::FR + NOV - 1;
-    static constexpr size_t FBUF = sizeof(float) * RING * FROW;
+    static constexpr size_t FBUF = Smem<G>::al16(sizeof(float) * RING * FROW);
     static constexpr size_t RED = sizeof(float2) * (G::NT / 32) * G::FR;
-    static constexpr size_t SYNTH = Smem<G>::ZB + FBUF + RED;
-    static constexpr size_t ADJ = Smem<G>::ZB + Smem<G>::STAGE + RED;
+    static constexpr size_t SYNTH = Smem<G>::ZB + FBUF + RED + Smem<G>::TABLES;
+    static constexpr size_t ADJ = Smem<G>::ZB + Smem<G>::STAGE + RED + Smem<G>::TABLES;
 };
 
 // per-frame parity sums across the CTA: every thread contributes its partial (e, o) for frame fr
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
     float* fbuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float2* red = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB + C::FBUF);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + C::FBUF + C::RED, tid);   // visible after the ring-zero barrier below
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const int nb = a.b_hi - a.b_lo;
     const int b0 = a.b_lo + (int)(((int64_t)chunk * nb) / a.nchunks);
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
     const int total = a.win_len + G::HOP * (a.nframe - 1);
     // ring slots 0..NOV-2 carry the previous group's last frames; zero them for the first group
     for (int i = tid; i < (C::NOV - 1) * C::FROW; i += G::NT) fbuf[i] = 0.f;
+    __syncthreads();
     for (int g = 0; g < ngroups; ++g) {
         const int f_base = f0 + g * G::FR;
         const int t = f_base + fr;
@@ -92,10 +94,10 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
             const int p = unit + i * G::NU;
             float2 ya[8], yb[8], nyq;
             load_task_planar<G>(spec, a.nframe, t, p, ya, yb, nyq);
-            synthesis_task<G>(zb, a.tb, p, fr, ya, yb, nyq);
+            synthesis_task<G>(zb, tb, p, fr, ya, yb, nyq);
         }
         __syncthreads();
-        passB_inv<G>(a.tb.tw, zb, unit, fr);
+        passB_inv<G>(tb.tw, zb, unit, fr);
         __syncthreads();
         // pass A' without the window: raw v[j]; parity sums over j < win_len
         float2 v[G::TA][G::R1];
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
 #pragma unroll
             for (int k = 0; k < G::R1; ++k) v[i][k] = zb[(u + 64 * k) * G::FR + fr];
 #pragma unroll
-            for (int k = 1; k < G::R1; ++k) v[i][k] = cmulc(v[i][k], __ldg(a.tb.tw + u * k));
+            for (int k = 1; k < G::R1; ++k) v[i][k] = cmulc(v[i][k], tb.tw[u * k]);
             dftR<G::R1, true>(v[i]);
 #pragma unroll
             for (int r = 0; r < G::R1; ++r) {
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
 #pragma unroll
             for (int r = 0; r < G::R1; ++r) {
                 const int j = 2 * (u + 64 * r);
-                const float2 w = __ldg(reinterpret_cast<const float2*>(a.tb.win + j));   // zero beyond win_len
+                const float2 w = *reinterpret_cast<const float2*>(tb.win + j);   // zero beyond win_len
                 *reinterpret_cast<float2*>(fbuf + (C::NOV - 1 + fr) * C::FROW + j) =
                     make_float2((v[i][r].x - ce) * w.x, (v[i][r].y - co) * w.y);
             }
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float2* red = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB + Smem<G>::STAGE);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE + C::RED, tid);
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const float* src = a.in + (size_t)row * a.out_len;
     float* out_row = a.out + (size_t)row * 2 * G::F * a.nframe;
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
             for (int r = 0; r < G::R1; ++r) {
                 const int j = 2 * (u + 64 * r);
                 const float2 x = *reinterpret_cast<const float2*>(stage + (fr + j / G::HOP) * G::SROW + j % G::HOP);
-                const float2 w = __ldg(reinterpret_cast<const float2*>(a.tb.win + j));
+                const float2 w = *reinterpret_cast<const float2*>(tb.win + j);
                 v[i][r] = make_float2(x.x * w.x, x.y * w.y);
                 part.x += v[i][r].x;          // window is zero beyond win_len
                 part.y += v[i][r].y;
@@ -219,19 +222,19 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
             }
             dftR<G::R1, false>(v[i]);
 #pragma unroll
-            for (int k = 1; k < G::R1; ++k) v[i][k] = cmul(v[i][k], __ldg(a.tb.tw + u * k));
+            for (int k = 1; k < G::R1; ++k) v[i][k] = cmul(v[i][k], tb.tw[u * k]);
 #pragma unroll
             for (int k = 0; k < G::R1; ++k) zb[(u + 64 * k) * G::FR + fr] = v[i][k];
         }
         __syncthreads();
-        passB_fwd<G>(a.tb.tw, zb, unit, fr);
+        passB_fwd<G>(tb.tw, zb, unit, fr);
         __syncthreads();
         const int t = f_base + fr;
 #pragma unroll
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
             float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
             store_task_planar<G>(out_row, a.nframe, t, p, xa, xb, nyq);
         }
         __syncthreads();

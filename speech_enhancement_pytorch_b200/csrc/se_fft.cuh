@@ -154,12 +154,12 @@ __device__ __forceinline__ void passA_fwd(const float* __restrict__ stage, const
         for (int r = 0; r < G::R1; ++r) {
             const int j = 2 * (u + 64 * r);
             const float2 x = *reinterpret_cast<const float2*>(stage + (fr + j / G::HOP) * G::SROW + j % G::HOP);
-            const float2 w = __ldg(reinterpret_cast<const float2*>(win + j));
+            const float2 w = *reinterpret_cast<const float2*>(win + j);
             a[r] = make_float2(x.x * w.x, x.y * w.y);
         }
         dftR<G::R1, false>(a);
 #pragma unroll
-        for (int k = 1; k < G::R1; ++k) a[k] = cmul(a[k], __ldg(tw + u * k));
+        for (int k = 1; k < G::R1; ++k) a[k] = cmul(a[k], tw[u * k]);
 #pragma unroll
         for (int k = 0; k < G::R1; ++k) zb[(u + 64 * k) * G::FR + fr] = a[k];
     }
@@ -170,7 +170,7 @@ __device__ __forceinline__ void passB_fwd(const float2* __restrict__ tw, float2*
     const int v = unit & 7;
     float2 t[8];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) t[k] = __ldg(tw + G::R1 * v * k);
+    for (int k = 1; k < 8; ++k) t[k] = tw[G::R1 * v * k];
 #pragma unroll
     for (int i = 0; i < G::TB; ++i) {
         const int k1 = (unit >> 3) + i * (G::NU / 8);
@@ -222,19 +222,19 @@ template <class G>
 __device__ __forceinline__ void split_task(int p, const float2* __restrict__ twn, float2* xa, float2* xb, float2& nyq) {
     if (p != 0) {
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) split_pair(xa[k4], xb[7 - k4], __ldg(twn + p + G::S * k4));
+        for (int k4 = 0; k4 < 8; ++k4) split_pair(xa[k4], xb[7 - k4], twn[p + G::S * k4]);
         nyq = make_float2(0.f, 0.f);
     } else {
         const float2 z0 = xa[0];
         xa[0] = make_float2(2.f * (z0.x + z0.y), 0.f);       // Z is pre-scaled by 1/2: E = 2 Re, O' = 2 Im
         nyq = make_float2(2.f * (z0.x - z0.y), 0.f);
 #pragma unroll
-        for (int k4 = 1; k4 < 4; ++k4) split_pair(xa[k4], xa[8 - k4], __ldg(twn + G::S * k4));
+        for (int k4 = 1; k4 < 4; ++k4) split_pair(xa[k4], xa[8 - k4], twn[G::S * k4]);
         float2 m0 = xa[4], m1 = xa[4];
-        split_pair(m0, m1, __ldg(twn + G::S * 4));
+        split_pair(m0, m1, twn[G::S * 4]);
         xa[4] = m0;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) split_pair(xb[k4], xb[7 - k4], __ldg(twn + G::S / 2 + G::S * k4));
+        for (int k4 = 0; k4 < 4; ++k4) split_pair(xb[k4], xb[7 - k4], twn[G::S / 2 + G::S * k4]);
     }
 }
 
@@ -242,17 +242,17 @@ template <class G>
 __device__ __forceinline__ void merge_task(int p, const float2* __restrict__ twn, float2* ya, float2* yb, float2 nyq) {
     if (p != 0) {
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) merge_pair(ya[k4], yb[7 - k4], __ldg(twn + p + G::S * k4));
+        for (int k4 = 0; k4 < 8; ++k4) merge_pair(ya[k4], yb[7 - k4], twn[p + G::S * k4]);
     } else {
         const float y0 = ya[0].x, ym = nyq.x;                   // imaginary parts of DC / Nyquist ignored
         ya[0] = make_float2(y0 + ym, y0 - ym);
 #pragma unroll
-        for (int k4 = 1; k4 < 4; ++k4) merge_pair(ya[k4], ya[8 - k4], __ldg(twn + G::S * k4));
+        for (int k4 = 1; k4 < 4; ++k4) merge_pair(ya[k4], ya[8 - k4], twn[G::S * k4]);
         float2 m0 = ya[4], m1 = ya[4];
-        merge_pair(m0, m1, __ldg(twn + G::S * 4));
+        merge_pair(m0, m1, twn[G::S * 4]);
         ya[4] = m0;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) merge_pair(yb[k4], yb[7 - k4], __ldg(twn + G::S / 2 + G::S * k4));
+        for (int k4 = 0; k4 < 4; ++k4) merge_pair(yb[k4], yb[7 - k4], twn[G::S / 2 + G::S * k4]);
     }
 }
 
@@ -270,7 +270,7 @@ __device__ __forceinline__ void passB_inv(const float2* __restrict__ tw, float2*
     const int v = unit & 7;
     float2 t[8];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) t[k] = __ldg(tw + G::R1 * v * k);
+    for (int k = 1; k < 8; ++k) t[k] = tw[G::R1 * v * k];
 #pragma unroll
     for (int i = 0; i < G::TB; ++i) {
         const int k1 = (unit >> 3) + i * (G::NU / 8);
@@ -293,11 +293,11 @@ __device__ __forceinline__ void passA_inv_task(const float2* __restrict__ zb, co
 #pragma unroll
     for (int k = 0; k < G::R1; ++k) a[k] = zb[(u + 64 * k) * G::FR + fr];
 #pragma unroll
-    for (int k = 1; k < G::R1; ++k) a[k] = cmulc(a[k], __ldg(tw + u * k));
+    for (int k = 1; k < G::R1; ++k) a[k] = cmulc(a[k], tw[u * k]);
     dftR<G::R1, true>(a);
 #pragma unroll
     for (int r = 0; r < G::R1; ++r) {
-        const float2 w = __ldg(reinterpret_cast<const float2*>(win + 2 * (u + 64 * r)));
+        const float2 w = *reinterpret_cast<const float2*>(win + 2 * (u + 64 * r));
         a[r] = make_float2(a[r].x * w.x, a[r].y * w.y);
     }
 }

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables ta = stage_tables<G>(a.ta, se_smem + Smem<G>::ZB + Smem<G>::IOBUF, tid);
+    const Tables ts = stage_window<G>(ta, a.ts, se_smem + Smem<G>::ZB + Smem<G>::IOBUF + Smem<G>::TABLES, tid);
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     AnaArgs la;
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
         const int tc = live ? t : 0;                       // clamped: loads stay in bounds, result zeroed
         fill_stage<G, LOAD_REFLECT>(iobuf, a.x + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
         __syncthreads();
-        analysis_passes<G>(iobuf, a.ta, zb, unit, fr);
+        analysis_passes<G>(iobuf, ta, zb, unit, fr);
 #pragma unroll
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
             }
             mn = load_mask<G, MODE>(a, row, G::M, tc);
             float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.ta, p, fr, xa, xb, nyq);
+            analysis_task<G>(zb, ta, p, fr, xa, xb, nyq);
             const float keep = live ? 1.f : 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -78,9 +80,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
             }
             nyq = MaskMath::apply<MODE, TANH>(nyq, mn);
             nyq = (p == 0) ? make_float2(nyq.x * keep, nyq.y * keep) : make_float2(0.f, 0.f);
-            synthesis_task<G>(zb, a.ts, p, fr, xa, xb, nyq);
+            synthesis_task<G>(zb, ts, p, fr, xa, xb, nyq);
         }
-        synthesis_tail<G>(zb, a.ts, iobuf, unit, fr, carry);
+        synthesis_tail<G>(zb, ts, iobuf, unit, fr, carry);
         emit_istft<G>(iobuf, out_row, f_base, c, sa, tid);
         __syncthreads();
     }
@@ -95,6 +97,8 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
     float2* zbg = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB);
     float* stage = reinterpret_cast<float*>(se_smem + 2 * Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables ta = stage_tables<G>(a.ta, se_smem + 2 * Smem<G>::ZB + Smem<G>::STAGE, tid);
+    const Tables ts = stage_window<G>(ta, a.ts, se_smem + 2 * Smem<G>::ZB + Smem<G>::STAGE + Smem<G>::TABLES, tid);
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     AnaArgs lx;
     lx.tb = a.ta; lx.nsample = a.nsample; lx.nframe = a.nframe; lx.in_len = a.nsample; lx.pad = 0;
@@ -108,10 +112,10 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
         const int tc = live ? t : 0;
         fill_stage<G, LOAD_REFLECT>(stage, a.x + (size_t)row * a.nsample, f_base * G::HOP, lx, tid);
         __syncthreads();
-        analysis_passes<G>(stage, a.ta, zbx, unit, fr);          // ends with a barrier: stage is free
+        analysis_passes<G>(stage, ta, zbx, unit, fr);          // ends with a barrier: stage is free
         fill_stage<G, LOAD_ENV>(stage, a.gy + (size_t)row * a.nsample, f_base * G::HOP, lg, tid);
         __syncthreads();
-        analysis_passes<G>(stage, a.ts, zbg, unit, fr);
+        analysis_passes<G>(stage, ts, zbg, unit, fr);
 #pragma unroll
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
@@ -124,8 +128,8 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
                 for (int k = 0; k < 8; ++k) m[k] = load_mask<G, MODE>(a, row, q + G::S * k, tc);
                 if (half == 0) mn = load_mask<G, MODE>(a, row, G::M, tc);
                 float2 xa[8], xb[8], xn, ga[8], gb[8], gn;
-                analysis_task<G>(zbx, a.ta, p, fr, xa, xb, xn);
-                analysis_task<G>(zbg, a.ts, p, fr, ga, gb, gn);
+                analysis_task<G>(zbx, ta, p, fr, xa, xb, xn);
+                analysis_task<G>(zbg, ts, p, fr, ga, gb, gn);
                 if (!live) continue;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {

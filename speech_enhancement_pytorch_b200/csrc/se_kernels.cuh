@@ -342,19 +342,55 @@ __device__ __forceinline__ void finish_adj(const float* __restrict__ hold, float
     }
 }
 
+// ------------------------------------------------------------------ tables in shared memory
+// window (N floats), exp(-2 pi i k/M) and exp(-2 pi i k/n) (M float2 each) are copied into shared memory
+// once per CTA (12 N bytes, 128-bit copies that hit L1 after the first CTA of an SM): every twiddle /
+// window read inside the passes is then an LDS broadcast instead of an L1-tagged global load (ncu:
+// long-scoreboard on those loads was the largest stall class, L1TEX the busiest unit).
+template <class G>
+__device__ __forceinline__ Tables stage_tables(const Tables& g, unsigned char* dst, int tid) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    const float4* w = reinterpret_cast<const float4*>(g.win);
+    const float4* t0 = reinterpret_cast<const float4*>(g.tw);
+    const float4* t1 = reinterpret_cast<const float4*>(g.twn);
+    constexpr int NW = G::N / 4, NTW = G::M / 2;
+    for (int i = tid; i < NW; i += G::NT) d[i] = __ldg(w + i);
+    for (int i = tid; i < NTW; i += G::NT) { d[NW + i] = __ldg(t0 + i); d[NW + NTW + i] = __ldg(t1 + i); }
+    Tables r = g;
+    r.win = reinterpret_cast<const float*>(dst);
+    r.tw = reinterpret_cast<const float2*>(dst + sizeof(float) * G::N);
+    r.twn = reinterpret_cast<const float2*>(dst + sizeof(float) * G::N + sizeof(float2) * G::M);
+    return r;
+}
+// second window only (fused kernels use an analysis and a synthesis window with shared twiddles)
+template <class G>
+__device__ __forceinline__ Tables stage_window(const Tables& staged, const Tables& g, unsigned char* dst, int tid) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    const float4* w = reinterpret_cast<const float4*>(g.win);
+    for (int i = tid; i < G::N / 4; i += G::NT) d[i] = __ldg(w + i);
+    Tables r = g;
+    r.win = reinterpret_cast<const float*>(dst);
+    r.tw = staged.tw;
+    r.twn = staged.twn;
+    return r;
+}
+
 // ------------------------------------------------------------------ smem carve-up
 template <class G> struct Smem {
+    static constexpr size_t al16(size_t b) { return (b + 15) / 16 * 16; }      // regions stay 16-byte aligned
     static constexpr size_t ZB = sizeof(float) * G::ZB_FLOATS;
-    static constexpr size_t STAGE = sizeof(float) * G::STAGE_FLOATS;
-    static constexpr size_t OSTAGE = sizeof(float) * G::OSTAGE_FLOATS;
-    static constexpr size_t HOLD = sizeof(float) * (G::N + 2 * G::HOP);
-    static constexpr size_t ANALYSIS = ZB + STAGE;
-    static constexpr size_t SYNTH_ISTFT = ZB + OSTAGE;
-    static constexpr size_t SYNTH_ADJ = ZB + OSTAGE + HOLD;
+    static constexpr size_t STAGE = al16(sizeof(float) * G::STAGE_FLOATS);
+    static constexpr size_t OSTAGE = al16(sizeof(float) * G::OSTAGE_FLOATS);
+    static constexpr size_t HOLD = al16(sizeof(float) * (G::N + 2 * G::HOP));
+    static constexpr size_t TABLES = sizeof(float) * G::N + 2 * sizeof(float2) * G::M;   // window + 2 twiddle tables
+    static constexpr size_t WINDOW = sizeof(float) * G::N;
+    static constexpr size_t ANALYSIS = ZB + STAGE + TABLES;
+    static constexpr size_t SYNTH_ISTFT = ZB + OSTAGE + TABLES;
+    static constexpr size_t SYNTH_ADJ = ZB + OSTAGE + HOLD + TABLES;
     // fused analysis+synthesis: stage and ostage are never live together -> aliased
     static constexpr size_t IOBUF = STAGE > OSTAGE ? STAGE : OSTAGE;
-    static constexpr size_t FUSED_ADJ = ZB + IOBUF + HOLD;
-    static constexpr size_t FUSED_ISTFT = ZB + IOBUF;
+    static constexpr size_t FUSED_ADJ = ZB + IOBUF + HOLD + TABLES;
+    static constexpr size_t FUSED_ISTFT = ZB + IOBUF + TABLES + WINDOW;
 };
 
 // ================================================================== kernels
@@ -365,6 +401,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);   // visible after the fill's barrier
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const int seg = row / a.seg_rows, clip = row - seg * a.seg_rows;
     const float* src = a.in + (size_t)seg * a.in_stride + (size_t)clip * a.clip_stride;
@@ -378,13 +415,13 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
         if (f_base >= a.nframe) break;
         fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid, nvalid);
         __syncthreads();
-        analysis_passes<G>(stage, a.tb, zb, unit, fr);
+        analysis_passes<G>(stage, tb, zb, unit, fr);
         const int t = f_base + fr;
         SE_TC_PRAGMA
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
             float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
             if (PLANAR) store_task_planar<G>(a.out + (size_t)row * 2 * G::F * a.nframe, a.nframe, t, p, xa, xb, nyq);
             else store_task_ft2<G>(reinterpret_cast<float2*>(a.out) + (size_t)row * G::F * a.nframe, a.nframe, t, p,
                                    xa, xb, nyq, a.edge_scale);
@@ -401,6 +438,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
     float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::OSTAGE);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::OSTAGE + (EMODE == EMIT_ADJ ? Smem<G>::HOLD : 0), tid);
+    __syncthreads();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     const float2* spec = reinterpret_cast<const float2*>(a.in) + (size_t)row * G::F * a.nframe;
@@ -418,9 +457,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
             const int p = unit + i * G::NU;
             float2 ya[8], yb[8], nyq;
             load_task_ft2<G>(spec, a.nframe, t, p, ya, yb, nyq, a.edge_scale);
-            synthesis_task<G>(zb, a.tb, p, fr, ya, yb, nyq);
+            synthesis_task<G>(zb, tb, p, fr, ya, yb, nyq);
         }
-        synthesis_tail<G>(zb, a.tb, ostage, unit, fr, carry);
+        synthesis_tail<G>(zb, tb, ostage, unit, fr, carry);
         if (EMODE == EMIT_ISTFT) emit_istft<G>(ostage, out_row, f_base, c, a, tid);
         else emit_adj<G>(ostage, hold, out_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
     }
@@ -456,6 +495,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     __shared__ float red[3][32];
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     AnaArgs la;
     la.tb = a.tb; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;
@@ -467,7 +507,6 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
         float pb[G::TC][17];
 #pragma unroll 1
         for (int sig = 0; sig < 2; ++sig) {              // 0: reference magnitudes, 1: estimate + statistics
-            const Tables tb = launder_tables(a.tb);
             fill_stage<G, LOAD_REFLECT>(stage, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
             __syncthreads();
             analysis_passes<G>(stage, tb, zb, unit, fr);
@@ -523,6 +562,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);          // stage, later ostage
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::IOBUF);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::IOBUF + Smem<G>::HOLD, tid);
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     AnaArgs la;
@@ -555,7 +595,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         }
         fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
         __syncthreads();
-        analysis_passes<G>(iobuf, a.tb, zb, unit, fr);
+        analysis_passes<G>(iobuf, tb, zb, unit, fr);
         SE_TC_PRAGMA
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
@@ -568,7 +608,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
             }
             mb[16] = __ldg(mrow + (size_t)G::M * a.nframe);
             float2 xa[8], xb[8], nyq;
-            analysis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
 #pragma unroll
             for (int k = 0; k < 17; ++k) {
                 float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
@@ -585,9 +625,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
                 v = make_float2(v.x * coef, v.y * coef);
                 if (k < 8) xa[k] = v; else if (k < 16) xb[k - 8] = v; else nyq = v;
             }
-            synthesis_task<G>(zb, a.tb, p, fr, xa, xb, nyq);
+            synthesis_task<G>(zb, tb, p, fr, xa, xb, nyq);
         }
-        synthesis_tail<G, false>(zb, a.tb, iobuf, unit, fr, nullptr);
+        synthesis_tail<G, false>(zb, tb, iobuf, unit, fr, nullptr);
         emit_adj<G>(iobuf, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
         __syncthreads();
     }

@@ -49,7 +49,7 @@ inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block
     emu::launch(dim3(grid), dim3(block), smem, [&]() { kern(args...); });
     return cudaSuccess;
 #else
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {      // static __shared__ counts against the 48 KB default too: opt in early
         // opt in to large dynamic shared memory once per (device, kernel); keeps the steady-state
         // launch path free of driver calls (and CUDA-graph capturable)
         static std::mutex mu;
