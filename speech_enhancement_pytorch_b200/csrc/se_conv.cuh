@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
     float* fbuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float2* red = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB + C::FBUF);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + C::FBUF + C::RED, tid);   // visible after the ring-zero barrier below
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const int nb = a.b_hi - a.b_lo;
     const int b0 = a.b_lo + (int)(((int64_t)chunk * nb) / a.nchunks);
@@ -167,7 +169,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float2* red = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB + Smem<G>::STAGE);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE + C::RED, tid);
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const float* src = a.in + (size_t)row * a.out_len;
     float* out_row = a.out + (size_t)row * 2 * G::F * a.nframe;

@@ -34,8 +34,10 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables ta = stage_tables<G>(a.ta, se_smem + Smem<G>::ZB + Smem<G>::IOBUF, tid);
     const Tables ts = stage_window<G>(ta, a.ts, se_smem + Smem<G>::ZB + Smem<G>::IOBUF + Smem<G>::TABLES, tid);
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     AnaArgs la;
@@ -97,8 +99,10 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
     float2* zbg = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB);
     float* stage = reinterpret_cast<float*>(se_smem + 2 * Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables ta = stage_tables<G>(a.ta, se_smem + 2 * Smem<G>::ZB + Smem<G>::STAGE, tid);
     const Tables ts = stage_window<G>(ta, a.ts, se_smem + 2 * Smem<G>::ZB + Smem<G>::STAGE + Smem<G>::TABLES, tid);
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     AnaArgs lx;
     lx.tb = a.ta; lx.nsample = a.nsample; lx.nframe = a.nframe; lx.in_len = a.nsample; lx.pad = 0;

@@ -401,7 +401,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);   // visible after the fill's barrier
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const int seg = row / a.seg_rows, clip = row - seg * a.seg_rows;
     const float* src = a.in + (size_t)seg * a.in_stride + (size_t)clip * a.clip_stride;
@@ -438,8 +440,10 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
     float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::OSTAGE);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::OSTAGE + (EMODE == EMIT_ADJ ? Smem<G>::HOLD : 0), tid);
     __syncthreads();
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     const float2* spec = reinterpret_cast<const float2*>(a.in) + (size_t)row * G::F * a.nframe;
@@ -495,7 +499,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     __shared__ float red[3][32];
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     AnaArgs la;
     la.tb = a.tb; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;
@@ -562,7 +568,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);          // stage, later ostage
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::IOBUF);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::IOBUF + Smem<G>::HOLD, tid);
+    pdl_wait();
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     AnaArgs la;
@@ -639,6 +647,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
 // reduce per-CTA partials -> sums[9] in a fixed order (one CTA per resolution, deterministic)
 static __global__ void k_reduce_partials(const double* __restrict__ partials, int n0, int n1, int n2, double* __restrict__ sums) {
     __shared__ double sh[3][256];
+    pdl_launch_dependents();
+    pdl_wait();
     const int tid = threadIdx.x, r = blockIdx.x;
     const int n = r == 0 ? n0 : (r == 1 ? n1 : n2);
     partials += (size_t)3 * (r == 0 ? 0 : (r == 1 ? n0 : n0 + n1));
@@ -656,6 +666,8 @@ static __global__ void k_reduce_partials(const double* __restrict__ partials, in
 }
 
 static __global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const double cnt[3] = {c0, c1, c2};
         double total = 0.0;
@@ -762,6 +774,8 @@ struct MaskMath {
 template <int MODE, bool TANH>
 __global__ void __launch_bounds__(256) k_mask_fwd_t(const float2* __restrict__ spec, const float* __restrict__ mask,
                                                     float2* __restrict__ out, int64_t count) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool vec = ((reinterpret_cast<uintptr_t>(spec) | reinterpret_cast<uintptr_t>(mask) |
@@ -792,6 +806,8 @@ template <int MODE, bool TANH>
 __global__ void __launch_bounds__(256) k_mask_bwd_t(const float2* __restrict__ spec, const float* __restrict__ mask,
                                                     const float2* __restrict__ gout, float* __restrict__ gmask,
                                                     float2* __restrict__ gspec, int64_t count) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool vec = ((reinterpret_cast<uintptr_t>(spec) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(gout) |

@@ -41,6 +41,21 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 #endif
 }
 
+// Programmatic dependent launch (sm_90+): every kernel lets its successor start launching as soon
+// as all of its own CTAs are resident, and waits for its predecessors right before it first touches
+// their output.  The successor's prologue (index setup, table staging into shared memory) and its
+// ramp-up then overlap the predecessor's partially filled last wave.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifndef SE_EMULATE
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#ifndef SE_EMULATE
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 template <class... Params, class... Args>
 inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block, size_t smem,
                           cudaStream_t stream, Args... args) {
@@ -64,8 +79,17 @@ inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block
             done.insert(key);
         }
     }
-    kern<<<grid, block, smem, stream>>>(args...);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
 #endif
 }
 
