@@ -53,7 +53,7 @@ extern "C" int se_conv_istft_fwd(const float* spec, float* y, int64_t rows, int6
     if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len)) return rc;
     a.in = spec; a.out = y;
     a.b_lo = a.pad / win_inc; a.b_hi = (int)((a.pad + out_len + win_inc - 1) / win_inc);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, 4);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, 4, 2);
     using G = Geo<512, 100, 256>;
     cudaError_t e = launch(k_conv_istft<G>, (unsigned)(rows * a.nchunks), G::NT, ConvGeo<G>::SYNTH, (cudaStream_t)stream, a);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_istft_fwd launch");

@@ -98,7 +98,8 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
         a.est = est; a.refmag = const_cast<float*>(refmag); a.g_est = g_est; a.sums = sums + 3 * r; a.gout = gout;
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
         a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
-        a.nchunks = (a.b_hi + 12) / 13;          // single-group chunks: 16 - (OLA-1) blocks each, no carry
+        a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
+                              : plan_synthesis(rows, a.b_hi, n / hop, n == 512 ? 2 : 1);
         a.accumulate = r > 0;
         a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
         a.inv_res = 1.0f / 3.0f;

@@ -60,7 +60,7 @@ int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, in
     a.in = gspec; a.out = gx; a.nsample = (int)nsample; a.out_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop);
     a.b_lo = 0; a.b_hi = (int)((nsample + n_fft + hop - 1) / hop);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop, n_fft >= 2048 ? 1 : 2);
     a.accumulate = accumulate; a.edge_scale = 2.0f;
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMIT_ADJ>(a, rows, (cudaStream_t)stream)));
@@ -79,7 +79,7 @@ int se_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int6
     a.in = spec; a.out = y; a.nsample = (int)(n_fft + hop * (nframe - 1)); a.out_len = (int)length;
     a.nframe = (int)nframe;
     a.b_lo = (n_fft / 2) / hop; a.b_hi = (int)((n_fft / 2 + length + hop - 1) / hop);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop, n_fft >= 2048 ? 1 : 2);
     a.accumulate = 0; a.edge_scale = 1.0f;
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMIT_ISTFT>(a, rows, (cudaStream_t)stream)));

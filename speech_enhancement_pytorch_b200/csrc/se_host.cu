@@ -3,6 +3,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -123,13 +124,26 @@ void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks) {
     gpc = (int)g;
     nchunks = (int)((ng + g - 1) / g);
 }
-int plan_synthesis(int64_t rows, int nb, int ola) {
-    int64_t ng = (nb + 15) / 16;
-    int64_t g = (rows * ng) / g_target_ctas;
-    g = g < 1 ? 1 : (g > 8 ? 8 : g);
-    const int cb_max = (int)(16 * g) - (ola - 1);
-    int nchunks = (nb + cb_max - 1) / cb_max;
-    return nchunks < 1 ? 1 : nchunks;
+// Pick the groups-per-chunk g that minimises (waves x g): a chunk of g groups emits 16 g - (ola-1)
+// blocks (the first ola-1 frames are halo recompute), so larger g wastes less, but the grid must still
+// fill the GPU in whole waves.  ctas_per_sm = resident CTAs of this kernel per SM.
+int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm) {
+    const int64_t slots = 148LL * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+    int best_chunks = 1;
+    double best_cost = 1e30;
+    // SE_FORCE_GROUPS=g pins the choice (tests exercise the multi-group carry path on tiny inputs)
+    const char* force = std::getenv("SE_FORCE_GROUPS");
+    const int g_lo = force ? std::atoi(force) : 1, g_hi = force ? std::atoi(force) : 8;
+    for (int g = (g_lo < 1 ? 1 : g_lo); g <= (g_hi > 8 ? 8 : g_hi); ++g) {
+        const int cb_max = 16 * g - (ola - 1);
+        const int nchunks = (nb + cb_max - 1) / cb_max;
+        const int cb = (nb + nchunks - 1) / nchunks;                 // even split (make_chunk)
+        const int groups = (cb + ola - 1 + 15) / 16;
+        const int64_t waves = (rows * nchunks + slots - 1) / slots;
+        const double cost = (double)waves * groups;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_chunks = nchunks; }
+    }
+    return best_chunks < 1 ? 1 : best_chunks;
 }
 
 int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length) {

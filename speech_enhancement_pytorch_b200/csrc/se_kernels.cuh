@@ -581,7 +581,14 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
     const float beta = gs * a.inv_count;
     float* gx_row = a.g_est + (size_t)row * a.nsample;
-    // chunks are planned as single groups (<= 16 - (OLA-1) emitted blocks): no OLA carry to keep live
+    // n = 2048 runs single-group chunks (no OLA carry to keep live in its tighter register budget);
+    // the smaller sizes carry the OLA tail across 2+ groups and recompute less halo
+    constexpr bool CARRY = G::N <= 1024;
+    float2 carry[CARRY ? G::TA : 1][G::SEG];
+#pragma unroll
+    for (int i = 0; i < (CARRY ? G::TA : 1); ++i)
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
     for (int g = 0; g < c.ngroups; ++g) {
         const int f_base = c.f0 + g * G::FR;
         const int t = f_base + fr;
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
             }
             synthesis_task<G>(zb, tb, p, fr, xa, xb, nyq);
         }
-        synthesis_tail<G, false>(zb, tb, iobuf, unit, fr, nullptr);
+        synthesis_tail<G, CARRY>(zb, tb, iobuf, unit, fr, carry);
         emit_adj<G>(iobuf, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
         __syncthreads();
     }

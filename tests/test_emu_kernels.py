@@ -191,3 +191,32 @@ def test_emu_segment_stft_matches_reference_segmenting():
     cfg = oref.make_config(512, 128, 512)
     want = oref.stft_custom_ref(torch.from_numpy(g["seg"]).reshape(nseg, wav.shape[0], nfeat), cfg).numpy()
     assert rel(got.reshape(want.shape), want) < 1e-6
+
+
+@pytest.mark.parametrize("groups", ["2", "3"])
+def test_emu_multi_group_chunks_carry_path(groups, monkeypatch):
+    """Force g groups per chunk so the OLA carry across groups (registers) is exercised on small inputs."""
+    monkeypatch.setenv("SE_FORCE_GROUPS", groups)
+    rng = np.random.default_rng(int(groups))
+    n, hop, win, N = 512, 128, 512, 9001
+    T, F = 1 + N // hop, n // 2 + 1
+    spec = rng.standard_normal((2, F, T)) + 1j * rng.standard_normal((2, F, T))
+    y = E.istft_fwd(r2(spec), N, n, hop, win, float(win))
+    assert rel(y, o64.istft(spec.astype(np.complex64), n, hop, win, N)) < 2e-6
+    gx = E.stft_bwd(r2(spec), N, n, hop, win, 1.0 / win)
+    assert rel(gx, o64.stft_adjoint(c2(r2(spec)), N, n, hop, win)) < 2e-6
+    ref = rng.standard_normal((2, N)).astype(np.float32)
+    est = (ref + 0.1 * rng.standard_normal((2, N))).astype(np.float32)
+    sums, loss = E.mrstft_fwd(est, ref)
+    l64, g64 = o64.mrstft_loss(est, ref, with_grad=True)
+    g = E.mrstft_bwd(est, ref, sums, 1.0)
+    assert not np.isnan(g).any()
+    assert rel(g, g64) < 2e-3
+    x = rng.standard_normal((2, N)).astype(np.float32)
+    m = rng.standard_normal((2, F, T, 2)).astype(np.float32)
+    import types
+    cfg = types.SimpleNamespace(n_fft=n, hop_length=hop, win_length=win, center=True)
+    yy = E.enhance_fwd(x, m, n, hop, win, 2, False)
+    yr = oref.istft_custom_ref(oref.mask_apply_ref(oref.stft_custom_ref(torch.from_numpy(x)[:, None].double(), cfg),
+                                                   torch.from_numpy(m)[:, None].double(), "C"), N, cfg)
+    assert rel(yy, yr.numpy()[:, 0]) < 2e-6
