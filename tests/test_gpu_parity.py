@@ -364,3 +364,60 @@ def test_evaluate_identity_property_like_reference_test(se):
         model=types.SimpleNamespace(name="dnn", segment=1.024, n_fft=512, hop_length=128, win_length=512, center=True))
     out = se.evaluate(mix, None, "cuda", config)
     assert float((out - mix).abs().max()) < 1e-5
+
+
+def test_cfg5_long_form_44k_stereo(se, oref):
+    """BASELINE cfg 5 shape: 44.1 kHz stereo 30 s clips (N = 1 323 000), n_fft 2048 / 1024, complex mask."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 2, 1323000, generator=g)
+    for n in (2048, 1024):
+        c = cfg(n, n // 4, n)
+        xs = x.cuda()
+        spec = se.stft_custom(xs, c)
+        assert spec.shape == (1, 2, n // 2 + 1, 1 + 1323000 // (n // 4), 2)
+        y = se.istft_custom(spec, 1323000, c)
+        assert float((y - xs).abs().max()) < 2e-5
+        # spot-check the spectrum against the oracle on a slice of frames (the oracle on 30 s is slow but fine)
+        ref = oref.stft_custom_ref(x[:, :1, :200000], c)
+        got = se.stft_custom(xs[:, :1, :200000].contiguous(), c)
+        assert rel(got, ref) < TOL_SPEC
+        mask = torch.rand(1, 2, n // 2 + 1, spec.shape[-2], 2, generator=g) * 2 - 1
+        y1 = se.enhance(xs, mask.cuda(), c, "C")
+        y2 = se.istft_custom(se.apply_mask(spec, mask.cuda(), "C"), 1323000, c)
+        assert float((y1 - y2).abs().max()) < 1e-5 * max(1.0, float(y2.abs().max()))
+
+
+def test_cfg4_dccrn_transforms_full_size(se):
+    """BASELINE cfg 4 shape: 16 x 4 s through ConvSTFT -> ConviSTFT(length=64000) ~ identity (SURVEY: 1.7e-6)."""
+    x = torch.randn(16, 1, 64000, device="cuda")
+    st = se.ConvSTFT(400, 100, 512, "hann", "complex")
+    ist = se.ConviSTFT(400, 100, 512, 64000, "hann", "complex")
+    spec = st(x)
+    assert spec.shape == (16, 514, 643)
+    y = ist(spec)
+    assert y.shape == (16, 1, 64000)
+    assert float((y - x).abs().max()) < 2e-5
+    with torch.autocast("cuda", dtype=torch.bfloat16):          # bf16 model, fp32 spectra
+        y16 = ist(st(x.bfloat16()))
+    assert y16.dtype == torch.float32
+
+
+def test_cfg1_and_cfg3_shapes(se, oref):
+    """cfg 1 (16x4 s, 512/128, real mask) and cfg 3 (128x4 s MR-STFT loss fwd+bwd) run at full size."""
+    c = cfg(512, 128, 512)
+    x = torch.randn(16, 1, 64000, device="cuda")
+    m = torch.rand(16, 1, 257, 501, device="cuda")
+    y = se.istft_custom(se.apply_mask(se.stft_custom(x, c), m, "real"), 64000, c)
+    y2 = se.enhance(x, m, c, "real")
+    assert float((y - y2).abs().max()) < 1e-5
+    ref = oref.istft_custom_ref(oref.mask_apply_ref(oref.stft_custom_ref(x[:2].cpu(), c), m[:2].cpu(), "real"), 64000, c)
+    assert rel(y[:2], ref) < TOL_SPEC
+    est = torch.randn(128, 1, 64000, device="cuda", requires_grad=True)
+    tgt = torch.randn(128, 1, 64000, device="cuda")
+    loss = se.loss_mrstft(est, tgt)
+    loss.backward()
+    assert torch.isfinite(loss) and torch.isfinite(est.grad).all()
+    # linearity of the backward in the upstream gradient
+    est2 = est.detach().clone().requires_grad_(True)
+    (3.0 * se.loss_mrstft(est2, tgt)).backward()
+    assert rel(est2.grad, 3.0 * est.grad) < 1e-5
