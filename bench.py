@@ -167,8 +167,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL chatter (even its version line) off stdout
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L = nv.lib()
