@@ -166,8 +166,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
+    saved_stdout = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL chatter (even its version line) off stdout
+        # NCCL prints its version banner on stdout when the communicator is created: park stdout on
+        # stderr for the run so that rank 0's stdout carries exactly one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L = nv.lib()
@@ -417,6 +422,9 @@ def run_ours(args):
         cpu_baseline = {"value": crow * N / SR / dt, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"{crow} of {rows} rows per step, 3 timed steps ({dt * 1e3:.0f} ms/step), torch CPU oracle"}
 
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
