@@ -8,7 +8,7 @@ static const int kRes[3][3] = {{512, 128, 512}, {1024, 256, 1024}, {2048, 512, 2
 #define SE_DISPATCH_LOSS_GEO(n_fft, CALL)                                              \
     do {                                                                               \
         if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                      \
-        else if (n_fft == 1024) { using G = Geo<1024, 256, 512>; CALL; }               \
+        else if (n_fft == 1024) { using G = Geo<1024, 256, 256>; CALL; }               \
         else { using G = Geo<2048, 512, 512>; CALL; }                                  \
     } while (0)
 
@@ -99,7 +99,7 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
         a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
         a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
-                              : plan_synthesis(rows, a.b_hi, n / hop, n == 512 ? 2 : 1);
+                              : plan_synthesis(rows, a.b_hi, n / hop, 2);
         a.accumulate = r > 0;
         a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
         a.inv_res = 1.0f / 3.0f;
