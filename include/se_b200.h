@@ -56,6 +56,16 @@ const char* se_last_error(void);
 int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop,
                 int win_length, float scale, void* stream);
 
+/* ---- magnitude features feeding the NN bodies, the reference's quirks kept:
+ * kind 0 power |re^2+im^2| (src/model/unet.py:40), 1 magnitude sqrt(re^2+im^2) (dnn.py:98),
+ * 2 amplitude |re^2-im^2| (dcunet.py:379, stft_rnn.py:119, mel_rnn.py:123), 3 crn sqrt(re^2-im^2)
+ * (crn.py:101; NaN where |im| > |re|, like the reference).
+ * se_magnitude_feature: spec [count,2] -> feat [count].
+ * se_stft_feature_fwd: se_stft_fwd that also writes feat [rows,F,T] from the bins in registers. */
+int se_magnitude_feature(const float* spec, float* feat, int64_t count, int kind, void* stream);
+int se_stft_feature_fwd(const float* x, float* spec, float* feat, int64_t rows, int64_t nsample, int n_fft,
+                        int hop, int win_length, float scale, int kind, void* stream);
+
 /* ---- evaluate()'s "segment then STFT" (src/evaluate.py:29-39,164-183) without materialising the
  * overlapping segments: x [nclip, clip_stride] holds clips of clip_len valid samples; segment s of
  * clip c is x[c, s*seg_stride : s*seg_stride + nsample] (zero beyond clip_len, like the reference's

@@ -117,6 +117,8 @@ def magnitude_feature_ref(spec: torch.Tensor, kind: str):
         return torch.sqrt(re ** 2 + im ** 2)
     if kind == "amplitude":
         return torch.abs(re ** 2 - im ** 2)
+    if kind == "crn":
+        return torch.sqrt(re ** 2 - im ** 2)            # src/model/crn.py:101 (NaN source, kept)
     raise ValueError(kind)
 
 

@@ -8,17 +8,18 @@ Public surface (all CUDA-only, no CPU fallback):
     stft_custom, istft_custom          src/evaluate.py:101-162
     evaluate, segment_stft             src/evaluate.py:10-98,164-183 (segment -> STFT without copies)
     apply_mask, apply_mask_dccrn       model forward tails
+    magnitude_feature, stft_custom_with_feature   NN input features
     loss_mrstft, MRSTFTLoss            loss_function(enhanced, sources) convention
     ConvSTFT, ConviSTFT                src/model/dccrn.py:669-747
     enhance                            fused stft_custom -> mask -> istft_custom
 """
-from .evaluate import stft_custom, istft_custom, evaluate, segment_stft, stitch_segments
-from .masking import apply_mask, apply_mask_dccrn
+from .evaluate import stft_custom, istft_custom, stft_custom_with_feature, evaluate, segment_stft, stitch_segments
+from .masking import apply_mask, apply_mask_dccrn, magnitude_feature
 from .loss import loss_mrstft, MRSTFTLoss
 from .dccrn import ConvSTFT, ConviSTFT
 from .fused import enhance
 from . import _native
 
-__all__ = ["stft_custom", "istft_custom", "evaluate", "segment_stft", "stitch_segments", "apply_mask", "apply_mask_dccrn", "loss_mrstft", "MRSTFTLoss",
+__all__ = ["stft_custom", "istft_custom", "stft_custom_with_feature", "magnitude_feature", "evaluate", "segment_stft", "stitch_segments", "apply_mask", "apply_mask_dccrn", "loss_mrstft", "MRSTFTLoss",
            "ConvSTFT", "ConviSTFT", "enhance"]
 __version__ = "0.1.0"

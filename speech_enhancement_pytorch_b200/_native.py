@@ -20,13 +20,14 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = (
-    "se_version", "se_last_error", "se_stft_fwd", "se_stft_segments_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
+    "se_version", "se_last_error", "se_stft_fwd", "se_stft_segments_fwd", "se_magnitude_feature", "se_stft_feature_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
     "se_mask_fwd", "se_mask_bwd", "se_mrstft_workspace_bytes", "se_mrstft_loss_fwd",
     "se_mrstft_loss_value", "se_mrstft_loss_bwd", "se_enhance_fwd", "se_enhance_bwd",
     "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
 )
 
 MASK_MODES = {"real": 0, "E": 1, "C": 2, "R": 3}
+FEATURE_KINDS = {"power": 0, "magnitude": 1, "amplitude": 2, "crn": 3}
 
 
 BUILD_DIR = os.path.join(_PKG, "build")
@@ -102,6 +103,8 @@ def lib():
             L.se_mrstft_workspace_bytes.argtypes = [_I64, _I64]
             L.se_stft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
             L.se_stft_segments_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
+            L.se_magnitude_feature.argtypes = [_PTR, _PTR, _I64, _INT, _PTR]
+            L.se_stft_feature_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _PTR]
             L.se_stft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _PTR]
             L.se_istft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
             L.se_istft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]

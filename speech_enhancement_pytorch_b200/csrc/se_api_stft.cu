@@ -30,6 +30,33 @@ int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int 
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_fwd launch");
 }
 
+int se_stft_feature_fwd(const float* x, float* spec, float* feat, int64_t rows, int64_t nsample, int n_fft, int hop,
+                        int win_length, float scale, int kind, void* stream) {
+    if (!x || !spec || !feat) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (kind < 0 || kind > 3) return fail(SE_ERR_UNSUPPORTED, "feature kind must be 0..3 (power, magnitude, amplitude, crn)");
+    if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
+    if (nsample <= n_fft / 2) return fail(SE_ERR_BAD_ARG, "reflect padding needs nsample > n_fft/2");
+    AnaArgs a{};
+    if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
+    a.in = x; a.out = spec; a.feat = feat; a.feat_kind = kind; a.in_stride = nsample; a.seg_rows = 1;
+    a.nsample = (int)nsample; a.in_len = (int)nsample;
+    a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
+    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
+    cudaError_t e;
+    SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_feature_fwd launch");
+}
+
+int se_magnitude_feature(const float* spec, float* feat, int64_t count, int kind, void* stream) {
+    if (!spec || !feat || count <= 0) return fail(SE_ERR_BAD_ARG, "null pointer or empty tensor");
+    if (kind < 0 || kind > 3) return fail(SE_ERR_UNSUPPORTED, "feature kind must be 0..3 (power, magnitude, amplitude, crn)");
+    int64_t blocks = (count / 2 + 255) / 256 + 1;
+    if (blocks > 148 * 12) blocks = 148 * 12;
+    cudaError_t e = launch(k_feature, (unsigned)blocks, 256, 0, (cudaStream_t)stream,
+                           reinterpret_cast<const float2*>(spec), feat, count, kind);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_magnitude_feature launch");
+}
+
 int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t nclip, int64_t clip_len, int64_t clip_stride,
                          int64_t seg_stride, int64_t nsample, int n_fft, int hop, int win_length, float scale, void* stream) {
     if (!x || !spec) return fail(SE_ERR_BAD_ARG, "null pointer");

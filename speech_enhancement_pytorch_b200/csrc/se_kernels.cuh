@@ -45,6 +45,8 @@ struct AnaArgs {            // analysis: waveform-like -> spectrum
     int pad;                // ZEROPAD: zeros in front
     int gpc, nchunks;       // groups per chunk, chunks per row
     float edge_scale;       // multiplies DC and Nyquist outputs
+    float* feat;            // optional second output [rows, F, T]: magnitude feature of the spectrum (a6)
+    int feat_kind;
 };
 
 struct SynArgs {            // synthesis: spectrum -> waveform-like
@@ -146,11 +148,42 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
     }
 }
 
+// ------------------------------------------------------------------ magnitude features
+// NN input features computed from the spectrum, quirks of the reference kept:
+//   0 power     |re^2 + im^2|      src/model/unet.py:40
+//   1 magnitude sqrt(re^2 + im^2)  src/model/dnn.py:98
+//   2 amplitude |re^2 - im^2|      src/model/dcunet.py:379, stft_rnn.py:119, mel_rnn.py:123   (sic)
+//   3 crn       sqrt(re^2 - im^2)  src/model/crn.py:101   (NaN where |im| > |re|, like the reference)
+__device__ __forceinline__ float feature_of(float2 x, int kind) {
+    const float a = x.x * x.x, b = x.y * x.y;
+    if (kind == 0) return fabsf(a + b);
+    if (kind == 1) return sqrtf(a + b);
+    if (kind == 2) return fabsf(a - b);
+    return sqrtf(a - b);
+}
+
+static __global__ void __launch_bounds__(256) k_feature(const float2* __restrict__ spec, float* __restrict__ feat,
+                                                 int64_t count, int kind) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = ((reinterpret_cast<uintptr_t>(spec) | reinterpret_cast<uintptr_t>(feat)) & 15) == 0;
+    const int64_t pairs = vec ? count / 2 : 0;
+    for (int64_t i = tid0; i < pairs; i += stride) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(spec) + i);
+        reinterpret_cast<float2*>(feat)[i] = make_float2(feature_of(make_float2(x.x, x.y), kind),
+                                                         feature_of(make_float2(x.z, x.w), kind));
+    }
+    for (int64_t i = 2 * pairs + tid0; i < count; i += stride) feat[i] = feature_of(__ldg(spec + i), kind);
+}
+
 // ------------------------------------------------------------------ spectrum row I/O
 // interleaved [F][T] float2
 template <class G>
 __device__ __forceinline__ void store_task_ft2(float2* __restrict__ row, int T, int t, int p,
-                                               const float2* xa, const float2* xb, float2 nyq, float edge) {
+                                               const float2* xa, const float2* xb, float2 nyq, float edge,
+                                               float* __restrict__ frow = nullptr, int kind = 0) {
     if (t < 0 || t >= T) return;
     const int qa = task_qa<G>(p), qb = task_qb<G>(p);
 #pragma unroll
@@ -159,8 +192,16 @@ __device__ __forceinline__ void store_task_ft2(float2* __restrict__ row, int T, 
         if (p == 0 && k4 == 0) v = make_float2(v.x * edge, 0.f);
         row[(size_t)(qa + G::S * k4) * T + t] = v;
         row[(size_t)(qb + G::S * k4) * T + t] = xb[k4];
+        if (frow) {                                   // the NN's input feature, written while the bin is in registers
+            frow[(size_t)(qa + G::S * k4) * T + t] = feature_of(v, kind);
+            frow[(size_t)(qb + G::S * k4) * T + t] = feature_of(xb[k4], kind);
+        }
     }
-    if (p == 0) row[(size_t)G::M * T + t] = make_float2(nyq.x * edge, 0.f);
+    if (p == 0) {
+        const float2 v = make_float2(nyq.x * edge, 0.f);
+        row[(size_t)G::M * T + t] = v;
+        if (frow) frow[(size_t)G::M * T + t] = feature_of(v, kind);
+    }
 }
 // planar [2F][T] floats (DCCRN)
 template <class G>
@@ -440,7 +481,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
             analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
             if (PLANAR) store_task_planar<G>(a.out + (size_t)row * 2 * G::F * a.nframe, a.nframe, t, p, xa, xb, nyq);
             else store_task_ft2<G>(reinterpret_cast<float2*>(a.out) + (size_t)row * G::F * a.nframe, a.nframe, t, p,
-                                   xa, xb, nyq, a.edge_scale);
+                                   xa, xb, nyq, a.edge_scale,
+                                   a.feat ? a.feat + (size_t)row * G::F * a.nframe : nullptr, a.feat_kind);
         }
         __syncthreads();
     }

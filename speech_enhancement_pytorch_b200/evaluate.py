@@ -28,6 +28,30 @@ def stft_custom(tensor, config):
     return spec.reshape(*lead, *spec.shape[1:])
 
 
+def stft_custom_with_feature(tensor, config, kind):
+    """`stft_custom` that also returns the model's magnitude feature [B,(S,)C,F,T],
+    written by the same kernel while each bin is still in registers."""
+    import torch
+    from . import _native as nv
+    if tensor.dim() not in (3, 4):
+        raise ValueError(f"stft_custom expects a 3-D or 4-D tensor, got {tensor.dim()}-D")
+    if kind not in nv.FEATURE_KINDS:
+        raise ValueError(f"unknown feature kind {kind!r}")
+    n_fft, hop, win = _cfg(config)
+    ops._check_cfg(n_fft, hop, win)
+    lead, nsample = tuple(tensor.shape[:-1]), tensor.shape[-1]
+    x = ops._as_f32(tensor).reshape(-1, nsample).contiguous()
+    nv.require_cuda_f32(x)
+    rows = x.shape[0]
+    nf, nt = n_fft // 2 + 1, 1 + nsample // hop
+    spec = torch.empty((rows, nf, nt, 2), dtype=torch.float32, device=x.device)
+    feat = torch.empty((rows, nf, nt), dtype=torch.float32, device=x.device)
+    with nv.on_device(x.device):
+        nv.check(nv.lib().se_stft_feature_fwd(x.data_ptr(), spec.data_ptr(), feat.data_ptr(), rows, nsample, n_fft, hop,
+                                              win, 1.0 / win, nv.FEATURE_KINDS[kind], nv.stream_ptr(x.device)))
+    return spec.reshape(*lead, nf, nt, 2), feat.reshape(*lead, nf, nt)
+
+
 def istft_custom(tensor, length, config):
     """[B,C,F,T,2] or [B,S,C,F,T,2] -> [B,(S,)C,length] (evaluate.py:130-162)."""
     if tensor.dim() not in (5, 6):

@@ -26,3 +26,21 @@ def apply_mask_dccrn(specs, mask_real, mask_imag, mode="E"):
     mask = torch.stack([mask_real, mask_imag], dim=-1)
     out = ops.mask_apply(spec, mask, mode, False)
     return torch.cat([out[..., 0], out[..., 1]], dim=1)
+
+
+def magnitude_feature(spec, kind):
+    """NN input feature of a spectrum [...,F,T,2] -> [...,F,T], the reference's quirks kept:
+    'power' |re^2+im^2| (unet.py:40), 'magnitude' sqrt(re^2+im^2) (dnn.py:98), 'amplitude' |re^2-im^2|
+    (dcunet.py:379 `Amplitude`, stft_rnn.py:119, mel_rnn.py:123), 'crn' sqrt(re^2-im^2) (crn.py:101)."""
+    from . import _native as nv
+    if kind not in nv.FEATURE_KINDS:
+        raise ValueError(f"unknown feature kind {kind!r}")
+    if spec.requires_grad:
+        raise NotImplementedError("magnitude_feature: the reference never differentiates the input spectrogram")
+    s = ops._as_f32(spec).contiguous()
+    nv.require_cuda_f32(s)
+    out = torch.empty(s.shape[:-1], dtype=torch.float32, device=s.device)
+    with nv.on_device(s.device):
+        nv.check(nv.lib().se_magnitude_feature(s.data_ptr(), out.data_ptr(), out.numel(), nv.FEATURE_KINDS[kind],
+                                               nv.stream_ptr(s.device)))
+    return out

@@ -421,3 +421,26 @@ def test_cfg1_and_cfg3_shapes(se, oref):
     est2 = est.detach().clone().requires_grad_(True)
     (3.0 * se.loss_mrstft(est2, tgt)).backward()
     assert rel(est2.grad, 3.0 * est.grad) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["power", "magnitude", "amplitude", "crn"])
+def test_magnitude_features(se, oref, kind):
+    """NN input features, quirks kept (|re^2-im^2|, sqrt(re^2-im^2) with its NaNs)."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 1, 16000, generator=g)
+    c = cfg(512, 128, 512)
+    ref_spec = oref.stft_custom_ref(x, c)
+    want = oref.magnitude_feature_ref(ref_spec, kind)
+    spec, feat = se.stft_custom_with_feature(x.cuda(), c, kind)
+    assert rel(spec, ref_spec) < TOL_SPEC
+    got2 = se.magnitude_feature(ref_spec.cuda(), kind)
+    for got in (feat, got2):
+        assert got.shape == want.shape
+        g_ = got.cpu()
+        if kind == "crn":
+            # sign of re^2-im^2 can flip within round-off: compare where the reference is comfortably real
+            safe = (ref_spec[..., 0] ** 2 - ref_spec[..., 1] ** 2) > 1e-6 * (ref_spec ** 2).sum(-1)
+            assert torch.isnan(got2.cpu()).eq(torch.isnan(want)).all()
+            assert float((g_[safe] - want[safe]).abs().max() / want[safe].abs().max()) < 1e-3
+        else:
+            assert rel(g_, want) < TOL_SPEC
