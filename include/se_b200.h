@@ -119,6 +119,19 @@ int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsampl
 int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* sums, const float* gout,
                        int64_t global_rows, int64_t rows, int64_t nsample, float* g_est, void* stream);
 
+/* ---- STFT-domain training losses against a WAVEFORM target: what
+ * loss_function(enhanced, stft_custom(sources)) computes with torch's mse_loss / l1_loss on
+ * [B,C,F,T,2] (src/solver.py:457-458,480; src/distrib.py:263-267), without materialising the target
+ * spectrum.  kind 0 = mse, 1 = l1.  fwd: enh [rows,F,T,2], target [rows,N] -> *sum_out (device double)
+ * = sum of squared / absolute differences over this rank's rows (the mean is sum / (global_rows*F*T*2);
+ * all-reduce the sums across ranks first).  bwd: genh [rows,F,T,2] = gout * d mean / d enh. */
+int64_t se_spectral_loss_workspace_bytes(int64_t rows, int64_t nsample, int hop);
+int se_spectral_loss_fwd(const float* enh, const float* target, int64_t rows, int64_t nsample, int n_fft, int hop,
+                         int win_length, float scale, int kind, double* sum_out, void* workspace, void* stream);
+int se_spectral_loss_bwd(const float* enh, const float* target, const float* gout, int64_t global_rows, int64_t rows,
+                         int64_t nsample, int n_fft, int hop, int win_length, float scale, int kind, float* genh,
+                         void* stream);
+
 /* ---- fused wave -> STFT -> mask -> iSTFT -> wave (stft_custom + model tail + istft_custom in
  * one launch; SURVEY.md 8b "se_enhance_fwd/bwd").  mask [rows,F,T] (REAL) or [rows,F,T,2].
  * The 1/win_length and win_length scales of the reference cancel and are not applied. */

@@ -32,3 +32,22 @@ class MRSTFTLoss(torch.nn.Module):
 
     def forward(self, enhanced, sources):
         return loss_mrstft(enhanced, sources, self.group)
+
+
+def loss_spectral(enhanced_spec, sources_wave, config, kind="mse", group=None):
+    """`loss_function(enhanced, stft_custom(sources, config))` for the reference's STFT-domain training
+    losses (`mse` / `l1`, src/distrib.py:263-267 applied at src/solver.py:457-458,480) with the target
+    spectrum never written to memory.
+
+    enhanced_spec [B,(S,)C,F,T,2]; sources_wave [B,(S,)C,N] -> 0-dim tensor, gradient to enhanced_spec."""
+    from .evaluate import _cfg
+    kinds = {"mse": 0, "l1": 1}
+    if kind not in kinds:
+        raise ValueError(f"unknown spectral loss {kind!r}")
+    n_fft, hop, win = _cfg(config)
+    n = sources_wave.shape[-1]
+    nf, nt = n_fft // 2 + 1, 1 + n // hop
+    if tuple(enhanced_spec.shape[-3:]) != (nf, nt, 2) or enhanced_spec.shape[:-3] != sources_wave.shape[:-1]:
+        raise ValueError(f"spectrum {tuple(enhanced_spec.shape)} does not match waveform {tuple(sources_wave.shape)}")
+    return ops.spectral_loss_rows(enhanced_spec.reshape(-1, nf, nt, 2), sources_wave.reshape(-1, n), n_fft, hop, win,
+                                  kinds[kind], group)

@@ -183,6 +183,50 @@ def mrstft_loss_rows(est_rows, ref_rows, group=None, global_rows=None):
     return _MRSTFT.apply(_as_f32(est_rows).contiguous(), _as_f32(ref_rows).contiguous(), group, global_rows)
 
 
+class _SpectralLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enh, target, n_fft, hop, win_length, kind, group):
+        nv.require_cuda_f32(enh, target)
+        rows, n = target.shape
+        L = nv.lib()
+        ws = torch.empty(max(int(L.se_spectral_loss_workspace_bytes(rows, n, hop)), 8), dtype=torch.uint8, device=enh.device)
+        total = torch.empty((), dtype=torch.float64, device=enh.device)
+        with nv.on_device(enh.device):
+            nv.check(L.se_spectral_loss_fwd(enh.data_ptr(), target.data_ptr(), rows, n, n_fft, hop, win_length,
+                                            1.0 / win_length, kind, total.data_ptr(), ws.data_ptr(),
+                                            nv.stream_ptr(enh.device)))
+        global_rows = rows
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(total, group=group)
+            global_rows = rows * dist.get_world_size(group)
+        ctx.save_for_backward(enh, target)
+        ctx.cfg = (n_fft, hop, win_length, kind, global_rows)
+        count = global_rows * (n_fft // 2 + 1) * (1 + n // hop) * 2
+        return (total / count).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        enh, target = ctx.saved_tensors
+        n_fft, hop, win_length, kind, global_rows = ctx.cfg
+        rows, n = target.shape
+        gout = gout.contiguous().float()
+        g = torch.empty_like(enh)
+        with nv.on_device(enh.device):
+            nv.check(nv.lib().se_spectral_loss_bwd(enh.data_ptr(), target.data_ptr(), gout.data_ptr(), global_rows, rows, n,
+                                                   n_fft, hop, win_length, 1.0 / win_length, kind, g.data_ptr(),
+                                                   nv.stream_ptr(enh.device)))
+        return g, None, None, None, None, None, None
+
+
+def spectral_loss_rows(enh_rows, target_rows, n_fft, hop, win_length, kind, group=None):
+    _check_cfg(n_fft, hop, win_length)
+    if target_rows.requires_grad:
+        raise NotImplementedError("spectral loss: gradient flows to the enhanced spectrum only")
+    return _SpectralLoss.apply(_as_f32(enh_rows).contiguous(), _as_f32(target_rows).contiguous(), n_fft, hop, win_length,
+                               kind, group)
+
+
 # ------------------------------------------------------------------ fused enhance
 class _Enhance(torch.autograd.Function):
     @staticmethod

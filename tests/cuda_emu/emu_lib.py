@@ -188,3 +188,17 @@ def stft_segments_fwd(x, nseg, seg_stride, nsample, n, hop, win, scale):
     check(lib().se_stft_segments_fwd(ptr(x), ptr(out), i64(nseg), i64(nclip), i64(clip_len), i64(clip_len),
                                      i64(seg_stride), i64(nsample), ci(n), ci(hop), ci(win), f32(scale), None))
     return out
+
+
+def spectral_loss(enh, target, n, hop, win, kind, gout=1.0):
+    rows, N = target.shape
+    lib().se_spectral_loss_workspace_bytes.restype = ctypes.c_int64
+    ws = np.zeros(lib().se_spectral_loss_workspace_bytes(i64(rows), i64(N), ci(hop)) // 8 + 1, np.float64)
+    total = np.full(1, np.nan, np.float64)
+    check(lib().se_spectral_loss_fwd(ptr(enh), ptr(target), i64(rows), i64(N), ci(n), ci(hop), ci(win), f32(1.0 / win),
+                                     ci(kind), ptr(total), ptr(ws), None))
+    g = np.full(enh.shape, np.nan, np.float32)
+    go = np.array([gout], np.float32)
+    check(lib().se_spectral_loss_bwd(ptr(enh), ptr(target), ptr(go), i64(rows), i64(rows), i64(N), ci(n), ci(hop), ci(win),
+                                     f32(1.0 / win), ci(kind), ptr(g), None))
+    return float(total[0]) / (enh.size), g

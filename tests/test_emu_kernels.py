@@ -220,3 +220,25 @@ def test_emu_multi_group_chunks_carry_path(groups, monkeypatch):
     yr = oref.istft_custom_ref(oref.mask_apply_ref(oref.stft_custom_ref(torch.from_numpy(x)[:, None].double(), cfg),
                                                    torch.from_numpy(m)[:, None].double(), "C"), N, cfg)
     assert rel(yy, yr.numpy()[:, 0]) < 2e-6
+
+
+@pytest.mark.parametrize("kind,fn", [(0, torch.nn.functional.mse_loss), (1, torch.nn.functional.l1_loss)])
+def test_emu_fused_spectral_loss(kind, fn):
+    """loss_function(enhanced, stft_custom(sources)) with the target spectrum kept in registers (8f-2)."""
+    rng = np.random.default_rng(kind)
+    n, hop, win, N = 512, 128, 512, 3001
+    cfg = oref.make_config(n, hop, win)
+    tgt = rng.standard_normal((2, N)).astype(np.float32)
+    tspec = oref.stft_custom_ref(torch.from_numpy(tgt)[:, None], cfg)[:, 0]
+    enh = (tspec.numpy() + 0.01 * rng.standard_normal(tspec.shape)).astype(np.float32)
+    loss, g = E.spectral_loss(np.ascontiguousarray(enh), tgt, n, hop, win, kind, 0.5)
+    et = torch.from_numpy(enh).double().requires_grad_(True)
+    want = fn(et, tspec.double())
+    (gw,) = torch.autograd.grad(0.5 * want, et)
+    assert abs(loss - float(want)) / float(want) < 1e-5
+    assert not np.isnan(g).any()
+    if kind == 0:
+        assert rel(g, gw.numpy()) < 1e-4
+    else:                                   # sign() flips only where |e - s| is at round-off level
+        same = np.sign(g) == np.sign(gw.numpy())
+        assert same.mean() > 0.999

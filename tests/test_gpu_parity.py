@@ -444,3 +444,27 @@ def test_magnitude_features(se, oref, kind):
             assert float((g_[safe] - want[safe]).abs().max() / want[safe].abs().max()) < 1e-3
         else:
             assert rel(g_, want) < TOL_SPEC
+
+
+@pytest.mark.parametrize("kind,fn", [("mse", torch.nn.functional.mse_loss), ("l1", torch.nn.functional.l1_loss)])
+@pytest.mark.parametrize("n,h", [(512, 128), (1024, 256)])
+def test_fused_spectral_loss(se, oref, kind, fn, n, h):
+    """8f-2: loss_function(enhanced, stft_custom(sources)) with torch's mse/l1 (src/distrib.py:263-267)."""
+    g = torch.Generator().manual_seed(n)
+    c = cfg(n, h, n)
+    src = torch.randn(3, 1, 16000, generator=g)
+    tspec = oref.stft_custom_ref(src, c)
+    enh = tspec + 0.05 * torch.randn(tspec.shape, generator=g)
+    er = enh.double().requires_grad_(True)
+    want = fn(er, tspec.double())
+    (gw,) = torch.autograd.grad(want, er)
+    ec = enh.cuda().requires_grad_(True)
+    got = se.loss_spectral(ec, src.cuda(), c, kind)
+    assert got.dim() == 0
+    assert abs(float(got) - float(want)) / float(want) < 1e-4
+    (gg,) = torch.autograd.grad(got, ec)
+    if kind == "mse":
+        assert rel(gg, gw) < TOL_GRAD
+    else:
+        assert float((torch.sign(gg.cpu()) == torch.sign(gw)).double().mean()) > 0.999
+        assert rel(gg.abs(), gw.abs()) < 1e-5
