@@ -132,6 +132,15 @@ int se_spectral_loss_bwd(const float* enh, const float* target, const float* gou
                          int64_t nsample, int n_fft, int hop, int win_length, float scale, int kind, float* genh,
                          void* stream);
 
+/* ---- time-domain SI-SNR: si_snr(s1, s2, eps=1e-8) / loss_sisdr, src/loss.py:14-29.
+ * fwd: s1, s2 [rows,N] -> dots [rows,3] (device double: <s1,s1>, <s1,s2>, <s2,s2>) and snr [rows]
+ * (10 log10(|s_target|^2 / (|e|^2 + eps) + eps)); the caller takes the mean (and the sign for loss_sisdr).
+ * bwd: g [rows,N] = gscale * gout * d snr_row / d s1 (gout a device scalar; gscale = -+1/rows). */
+int se_sisnr_fwd(const float* s1, const float* s2, int64_t rows, int64_t nsample, double eps, double* dots,
+                 float* snr, void* stream);
+int se_sisnr_bwd(const float* s1, const float* s2, const double* dots, const float* gout, float gscale,
+                 int64_t rows, int64_t nsample, double eps, float* g, void* stream);
+
 /* ---- fused wave -> STFT -> mask -> iSTFT -> wave (stft_custom + model tail + istft_custom in
  * one launch; SURVEY.md 8b "se_enhance_fwd/bwd").  mask [rows,F,T] (REAL) or [rows,F,T,2].
  * The 1/win_length and win_length scales of the reference cancel and are not applied. */

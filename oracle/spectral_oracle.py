@@ -271,3 +271,38 @@ def audio_seconds(rows_shape, sample_rate):
     """audio-seconds = clips * N / sample_rate (channels do not multiply)."""
     nbatch, nsample = rows_shape[0], rows_shape[-1]
     return nbatch * nsample / float(sample_rate)
+
+
+def collate_fn_pad_ref(batch, segment_length, drop_last=True):
+    """src/distrib.py:38-98 (+ pad_last, src/utils.py:12-15): pad short clips to one segment, drop or
+    zero-pad the remainder, cut into segments, concatenate over the batch."""
+    mixes, srcs, index_batch = [], [], []
+    for item in batch:
+        mixture, sources = item[0], item[1]
+        if mixture.shape[-1] < segment_length:
+            mixture = F.pad(mixture, [0, segment_length - mixture.shape[-1]])
+            sources = F.pad(sources, [0, segment_length - sources.shape[-1]])
+        rem = mixture.shape[-1] % segment_length
+        if rem and drop_last:
+            keep = segment_length * (mixture.shape[-1] // segment_length)
+            mixture, sources = mixture[..., :keep], sources[..., :keep]
+        elif rem:
+            mixture = F.pad(mixture, [0, segment_length - rem])
+            sources = F.pad(sources, [0, segment_length - rem])
+        nch, length = mixture.shape
+        nseg = length // segment_length
+        mixes.append(mixture.reshape(nch, nseg, segment_length))
+        srcs.append(sources.reshape(sources.shape[0], nch, nseg, segment_length))
+        index_batch.append(nseg)
+    return torch.cat(mixes, 1).permute(1, 0, 2), torch.cat(srcs, 2).permute(2, 0, 1, 3), index_batch
+
+
+def si_snr_ref(s1, s2, eps=1e-8):
+    """src/loss.py:17-29."""
+    dot = torch.sum(s1 * s2, -1, keepdim=True)
+    s2s2 = torch.sum(s2 * s2, -1, keepdim=True)
+    s_target = dot / (s2s2 + eps) * s2
+    e_noise = s1 - s_target
+    tn = torch.sum(s_target * s_target, -1, keepdim=True)
+    nn_ = torch.sum(e_noise * e_noise, -1, keepdim=True)
+    return torch.mean(10 * torch.log10(tn / (nn_ + eps) + eps))

@@ -51,3 +51,17 @@ def loss_spectral(enhanced_spec, sources_wave, config, kind="mse", group=None):
         raise ValueError(f"spectrum {tuple(enhanced_spec.shape)} does not match waveform {tuple(sources_wave.shape)}")
     return ops.spectral_loss_rows(enhanced_spec.reshape(-1, nf, nt, 2), sources_wave.reshape(-1, n), n_fft, hop, win,
                                   kinds[kind], group)
+
+
+def si_snr(s1, s2, eps=1e-8):
+    """`si_snr(s1, s2, eps)` of src/loss.py:21-29 (mean scale-invariant SNR in dB over all rows) in one pass
+    over the two waveforms.  s1, s2 [...,N]."""
+    if s1.shape != s2.shape:
+        raise ValueError(f"shape mismatch {tuple(s1.shape)} vs {tuple(s2.shape)}")
+    n = s1.shape[-1]
+    return ops.si_snr_rows(s1.reshape(-1, n), s2.reshape(-1, n), eps)
+
+
+def loss_sisdr(inputs, targets):
+    """`loss_sisdr` of src/loss.py:14-15."""
+    return -si_snr(inputs, targets)

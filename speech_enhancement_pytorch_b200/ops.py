@@ -227,6 +227,38 @@ def spectral_loss_rows(enh_rows, target_rows, n_fft, hop, win_length, kind, grou
                                kind, group)
 
 
+class _SiSnr(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s1, s2, eps):
+        nv.require_cuda_f32(s1, s2)
+        rows, n = s1.shape
+        dots = torch.empty(rows, 3, dtype=torch.float64, device=s1.device)
+        snr = torch.empty(rows, dtype=torch.float32, device=s1.device)
+        with nv.on_device(s1.device):
+            nv.check(nv.lib().se_sisnr_fwd(s1.data_ptr(), s2.data_ptr(), rows, n, float(eps), dots.data_ptr(), snr.data_ptr(),
+                                           nv.stream_ptr(s1.device)))
+        ctx.save_for_backward(s1, s2, dots)
+        ctx.eps = float(eps)
+        return snr.mean()
+
+    @staticmethod
+    def backward(ctx, gout):
+        s1, s2, dots = ctx.saved_tensors
+        rows, n = s1.shape
+        g = torch.empty_like(s1)
+        gout = gout.contiguous().float()
+        with nv.on_device(s1.device):
+            nv.check(nv.lib().se_sisnr_bwd(s1.data_ptr(), s2.data_ptr(), dots.data_ptr(), gout.data_ptr(), 1.0 / rows, rows, n,
+                                           ctx.eps, g.data_ptr(), nv.stream_ptr(s1.device)))
+        return g, None, None
+
+
+def si_snr_rows(s1_rows, s2_rows, eps=1e-8):
+    if s2_rows.requires_grad:
+        raise NotImplementedError("si_snr: gradient flows to the first argument only")
+    return _SiSnr.apply(_as_f32(s1_rows).contiguous(), _as_f32(s2_rows).contiguous(), eps)
+
+
 # ------------------------------------------------------------------ fused enhance
 class _Enhance(torch.autograd.Function):
     @staticmethod

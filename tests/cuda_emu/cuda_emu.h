@@ -105,12 +105,12 @@ static inline int emu_warp_base() { return (int)(threadIdx.x - threadIdx.x % 32)
 
 template <class T>
 static inline T emu_shfl_abs(T v, int src_lane) {
-    static_assert(sizeof(T) == 4, "4-byte shuffles only");
-    uint32_t b;
-    std::memcpy(&b, &v, 4);
-    b = emu::exchange(b, emu_warp_base() + src_lane);
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte shuffles only");
+    uint32_t b[2] = {0, 0};
+    std::memcpy(b, &v, sizeof(T));
+    for (size_t w = 0; w < sizeof(T) / 4; ++w) b[w] = emu::exchange(b[w], emu_warp_base() + src_lane);
     T r;
-    std::memcpy(&r, &b, 4);
+    std::memcpy(&r, b, sizeof(T));
     return r;
 }
 template <class T>

@@ -468,3 +468,22 @@ def test_fused_spectral_loss(se, oref, kind, fn, n, h):
     else:
         assert float((torch.sign(gg.cpu()) == torch.sign(gw)).double().mean()) > 0.999
         assert rel(gg.abs(), gw.abs()) < 1e-5
+
+
+@pytest.mark.parametrize("shape,noise", [((4, 1, 16000), 0.3), ((2, 2, 1, 64000), 0.01), ((3, 1, 4001), 1.0)])
+def test_si_snr_and_gradient(se, oref, shape, noise):
+    """8f-4: si_snr / loss_sisdr (src/loss.py:14-29) in one pass, gradient A s1 + B s2."""
+    g = torch.Generator().manual_seed(shape[-1])
+    tgt = torch.randn(*shape, generator=g)
+    est = tgt * 0.7 + noise * torch.randn(*shape, generator=g)
+    er = est.double().requires_grad_(True)
+    want = oref.si_snr_ref(er, tgt.double())
+    (gw,) = torch.autograd.grad(-want, er)
+    ec = est.cuda().requires_grad_(True)
+    got = se.loss_sisdr(ec, tgt.cuda())
+    assert got.dim() == 0
+    assert abs(float(got) + float(want)) < 1e-3 * max(1.0, abs(float(want)))
+    (gg,) = torch.autograd.grad(got, ec)
+    assert rel(gg, gw) < TOL_GRAD
+    # against the reference's own fp32 evaluation
+    assert abs(float(got) + float(oref.si_snr_ref(est, tgt))) < 1e-3 * max(1.0, abs(float(want)))
