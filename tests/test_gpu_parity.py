@@ -487,3 +487,35 @@ def test_si_snr_and_gradient(se, oref, shape, noise):
     assert rel(gg, gw) < TOL_GRAD
     # against the reference's own fp32 evaluation
     assert abs(float(got) + float(oref.si_snr_ref(est, tgt))) < 1e-3 * max(1.0, abs(float(want)))
+
+
+def test_reentrant_from_threads_on_separate_streams(se, oref):
+    """nn.DataParallel runs DCCRN's transforms from one Python thread per GPU (src/solver.py:145): the C-ABI
+    must be re-entrant.  Two threads, two streams, different configurations, results checked per thread."""
+    import threading
+    g = torch.Generator().manual_seed(12)
+    xs = [torch.randn(4, 1, 16000, generator=g) for _ in range(2)]
+    cfgs = [cfg(512, 128, 512), cfg(1024, 256, 1024)]
+    refs = [oref.stft_custom_ref(x, c) for x, c in zip(xs, cfgs)]
+    out, err = [None, None], []
+
+    def work(i):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                x = xs[i].cuda()
+                for _ in range(20):
+                    spec = se.stft_custom(x, cfgs[i])
+                    y = se.istft_custom(spec, 16000, cfgs[i])
+                stream.synchronize()
+                out[i] = (spec.cpu(), float((y - x).abs().max()))
+        except Exception as e:      # noqa: BLE001
+            err.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not err, err
+    for i in range(2):
+        assert rel(out[i][0], refs[i]) < TOL_SPEC
+        assert out[i][1] < 1e-5
