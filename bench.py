@@ -376,6 +376,9 @@ def run_ours(args):
         h2d = (hx[0].numel() + hc[0].numel() + hm[0].numel()) * 4
         e2e = {"value": audio_s / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+               "h2d_gbs": round(h2d / (e2e_ms * 1e-3) * 1e-9, 1),
+               "note": "copy-bound: the 98.7 MB/step of pinned-host inputs (mixture, clean, raw mask) saturate PCIe; "
+                       "kernels overlap underneath on the compute stream",
                "api": "stft_custom/apply_mask/istft_custom/loss_mrstft + autograd; pinned host inputs, copy stream double-buffered",
                "loss": float(hloss)}
 
