@@ -53,26 +53,32 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
                        void* workspace, void* stream) {
     if (!est || !ref || !sums || !workspace) return fail(SE_ERR_BAD_ARG, "null pointer");
     if (rows <= 0 || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need rows > 0 and nsample >= 2048");
-    double* part = reinterpret_cast<double*>(workspace);
-    float* refmag = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + loss_partials_bytes(rows, nsample));
-    int nres[3] = {0, 0, 0};
+    double* part0 = reinterpret_cast<double*>(workspace);
+    float* refmag0 = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + loss_partials_bytes(rows, nsample));
+    int nres[3] = {0, 0, 0}, gpcs[3], nchs[3];
     for (int r = 0; r < 3; ++r) {
+        if (int rc = check_common(rows, nsample, kRes[r][0], kRes[r][1], kRes[r][2])) return rc;
+        nres[r] = loss_fwd_plan(rows, nsample, r, gpcs[r], nchs[r]);
+    }
+    // largest transform first; each follower starts in the previous kernel's tail (see k_loss_fwd)
+    for (int r = 2; r >= 0; --r) {
         const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
-        if (int rc = check_common(rows, nsample, n, hop, win)) return rc;
         LossArgs a{};
         if (int rc = get_tables(n, hop, win, false, 0.5f, a.tb)) return rc;
+        double* part = part0;
+        float* refmag = refmag0;
+        for (int q = 0; q < r; ++q) { part += (size_t)nres[q] * 3; refmag += loss_refmag_floats(rows, nsample, q); }
         a.est = est; a.ref = ref; a.partials = part; a.refmag = refmag;
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
-        const int nctas = loss_fwd_plan(rows, nsample, r, a.gpc, a.nchunks);
+        a.gpc = gpcs[r]; a.nchunks = nchs[r];
+        a.chained = r != 2;
         cudaError_t e;
         SE_DISPATCH_LOSS_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd launch");
-        nres[r] = nctas;
-        part += (size_t)nctas * 3;
-        refmag += loss_refmag_floats(rows, nsample, r);
     }
-    cudaError_t e = launch(k_reduce_partials, 3u, 256u, 0, (cudaStream_t)stream,
-                           (const double*)reinterpret_cast<double*>(workspace), nres[0], nres[1], nres[2], sums);
+    // plain stream serialisation: the reduction needs ALL three kernels, not just its immediate predecessor
+    cudaError_t e = launch_ex(false, k_reduce_partials, 3u, 256u, 0, (cudaStream_t)stream,
+                              (const double*)part0, nres[0], nres[1], nres[2], sums);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_fwd reduce launch");
 }
 

@@ -543,6 +543,7 @@ struct LossArgs {
     int gpc, nchunks;        // fwd chunking (analysis style)
     int b_lo, b_hi;          // bwd chunking (synthesis style)
     int accumulate;
+    int chained;             // fwd: 1 = independent follower of the previous loss-fwd kernel (see k_loss_fwd)
     float inv_count;         // 1 / (global_rows * F * T)
     float inv_res;           // 1 / number of resolutions
 };
@@ -555,9 +556,12 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     __shared__ float red[3][32];
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
-    pdl_launch_dependents();
+    // The three resolutions are independent of each other (disjoint outputs): they are launched largest first
+    // and chained so that the next one fills the SMs the previous one's last wave leaves idle.  The head of
+    // the chain releases its follower only AFTER its own dependencies are met, so followers need not wait.
+    if (a.chained) pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);
-    pdl_wait();
+    if (!a.chained) { pdl_wait(); pdl_launch_dependents(); }
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     AnaArgs la;
     la.tb = a.tb; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;

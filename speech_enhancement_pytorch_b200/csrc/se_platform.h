@@ -56,11 +56,13 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// pdl = true: the kernel may start while its stream predecessor is still running (it must call
+// pdl_wait() before touching the predecessor's output); pdl = false: classic stream serialisation.
 template <class... Params, class... Args>
-inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block, size_t smem,
-                          cudaStream_t stream, Args... args) {
+inline cudaError_t launch_ex(bool pdl, void (*kern)(Params...), unsigned grid, unsigned block, size_t smem,
+                             cudaStream_t stream, Args... args) {
 #ifdef SE_EMULATE
-    (void)stream;
+    (void)stream; (void)pdl;
     emu::launch(dim3(grid), dim3(block), smem, [&]() { kern(args...); });
     return cudaSuccess;
 #else
@@ -86,11 +88,17 @@ inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<Params>(args)...);
 #endif
+}
+
+template <class... Params, class... Args>
+inline cudaError_t launch(void (*kern)(Params...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                          Args... args) {
+    return launch_ex(true, kern, grid, block, smem, stream, args...);
 }
 
 }  // namespace se
