@@ -95,24 +95,29 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
                        int64_t rows, int64_t nsample, float* g_est, void* stream) {
     if (!est || !workspace || !sums || !gout || !g_est) return fail(SE_ERR_BAD_ARG, "null pointer");
     if (rows <= 0 || global_rows < rows || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need 0 < rows <= global_rows, nsample >= 2048");
-    const float* refmag = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + loss_partials_bytes(rows, nsample));
-    for (int r = 0; r < 3; ++r) {
+    const float* refmag0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + loss_partials_bytes(rows, nsample));
+    for (int r = 0; r < 3; ++r)
+        if (int rc = check_common(rows, nsample, kRes[r][0], kRes[r][1], kRes[r][2])) return rc;
+    // largest transform first; followers start in the previous kernel's tail and wait only before they
+    // accumulate into g_est (see k_loss_bwd)
+    for (int r = 2; r >= 0; --r) {
         const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
-        if (int rc = check_common(rows, nsample, n, hop, win)) return rc;
         LossArgs a{};
         if (int rc = get_tables(n, hop, win, false, 0.5f, a.tb)) return rc;
+        const float* refmag = refmag0;
+        for (int q = 0; q < r; ++q) refmag += loss_refmag_floats(rows, nsample, q);
         a.est = est; a.refmag = const_cast<float*>(refmag); a.g_est = g_est; a.sums = sums + 3 * r; a.gout = gout;
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
         a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
         a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
                               : plan_synthesis(rows, a.b_hi, n / hop, 2);
-        a.accumulate = r > 0;
+        a.accumulate = r != 2;
+        a.chained = r != 2;
         a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
         a.inv_res = 1.0f / 3.0f;
         cudaError_t e;
         SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd<G>(a, rows, (cudaStream_t)stream)));
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_bwd launch");
-        refmag += loss_refmag_floats(rows, nsample, r);
     }
     return 0;
 }

@@ -628,9 +628,13 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);          // stage, later ostage
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::IOBUF);
     const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
-    pdl_launch_dependents();
+    // Chained like the forward kernels (largest first).  Followers accumulate into g_est, which their
+    // predecessor writes: they run their whole first group (analysis + synthesis) before waiting, right
+    // in front of the first read-modify-write.
+    if (a.chained) pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::IOBUF + Smem<G>::HOLD, tid);
-    pdl_wait();
+    if (!a.chained) { pdl_wait(); pdl_launch_dependents(); }
+    bool must_wait = a.chained != 0;
     const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
     const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
     AnaArgs la;
@@ -718,6 +722,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
             synthesis_task<G>(zb, tb, p, fr, xa, xb, nyq);
         }
         synthesis_tail<G, CARRY>(zb, tb, iobuf, unit, fr, carry);
+        if (must_wait) { pdl_wait(); must_wait = false; }
         emit_adj<G>(iobuf, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
         __syncthreads();
     }
