@@ -88,7 +88,26 @@ int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out
 
 // torch.istft's "window overlap add min" check, evaluated on the host (no device sync):
 // the envelope depends only on the configuration.
+static bool envelope_ok_uncached(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_);
+
 bool envelope_ok(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_) {
+    // the answer depends only on the configuration: remember it (the check runs on every iSTFT call)
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int, int, int64_t, int64_t, int64_t>, bool> seen;
+    const auto key = std::make_tuple(n, hop, win_len, front ? 1 : 0, T, lo, hi);
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = seen.find(key);
+        if (it != seen.end()) return it->second;
+    }
+    const bool ok = envelope_ok_uncached(n, hop, win_len, front, T, lo, hi, floor_);
+    std::lock_guard<std::mutex> lock(mu);
+    if (seen.size() > 4096) seen.clear();
+    seen[key] = ok;
+    return ok;
+}
+
+static bool envelope_ok_uncached(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_) {
     std::vector<double> w;
     host_window(n, win_len, front, w);
     const int ola = (n + hop - 1) / hop;
