@@ -16,7 +16,7 @@ extern "C" int se_conv_stft_fwd(const float* x, float* spec, int64_t rows, int64
     if (int rc = get_tables(fft_len, win_inc, win_len, true, 0.5f, a.tb)) return rc;
     a.in = x; a.out = spec; a.in_stride = nsample; a.seg_rows = 1; a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)T; a.pad = pad; a.edge_scale = 1.0f;
-    plan_analysis(rows, T, a.gpc, a.nchunks);
+    plan_analysis(rows, T, a.gpc, a.nchunks, 16);
     cudaError_t e;
     if (win_inc == 100) {
         using G = Geo<512, 100, 256>;
@@ -53,7 +53,7 @@ extern "C" int se_conv_istft_fwd(const float* spec, float* y, int64_t rows, int6
     if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len)) return rc;
     a.in = spec; a.out = y;
     a.b_lo = a.pad / win_inc; a.b_hi = (int)((a.pad + out_len + win_inc - 1) / win_inc);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, 4, 2);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, 4, 2, 16);
     using G = Geo<512, 100, 256>;
     cudaError_t e = launch(k_conv_istft<G>, (unsigned)(rows * a.nchunks), G::NT, ConvGeo<G>::SYNTH, (cudaStream_t)stream, a);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_istft_fwd launch");
@@ -65,7 +65,7 @@ extern "C" int se_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, in
     ConvArgs a{};
     if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len)) return rc;
     a.in = gy; a.out = gspec;
-    plan_analysis(rows, nframe, a.gpc, a.nchunks);
+    plan_analysis(rows, nframe, a.gpc, a.nchunks, 16);
     using G = Geo<512, 100, 256>;
     cudaError_t e = launch(k_conv_istft_adj<G>, (unsigned)(rows * a.nchunks), G::NT, ConvGeo<G>::ADJ, (cudaStream_t)stream, a);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_istft_bwd launch");

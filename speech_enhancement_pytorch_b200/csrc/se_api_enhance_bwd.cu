@@ -5,7 +5,8 @@
 using namespace se;
 
 template <class G>
-static cudaError_t run_enhance_bwd(const EnhArgs& a, int64_t rows, cudaStream_t st) {
+static cudaError_t run_enhance_bwd(EnhArgs a, int64_t rows, cudaStream_t st) {
+    plan_analysis(rows, a.nframe, a.gpc, a.nchunks, G::FR);
     cudaError_t e;
     SE_DISPATCH_MASK(a.mode, a.pre_tanh, (e = launch(k_enhance_bwd<G, MODE, TANH>, (unsigned)(rows * a.nchunks), G::NT,
                                                      2 * Smem<G>::ZB + Smem<G>::STAGE + Smem<G>::TABLES + Smem<G>::WINDOW, st, a)));
@@ -24,7 +25,6 @@ extern "C" int se_enhance_bwd(const float* gy, const float* x, const float* mask
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f / (float)win_length, a.ta)) return rc;
     if (int rc = get_tables(n_fft, hop, win_length, false, (float)win_length / (float)n_fft, a.ts)) return rc;
     a.x = x; a.mask = mask; a.gy = gy; a.out = gmask; a.nsample = (int)nsample; a.nframe = (int)T;
-    plan_analysis(rows, T, a.gpc, a.nchunks);
     a.mode = mode; a.pre_tanh = pre_tanh;
     cudaError_t e;
     if (n_fft == 512 && hop == 128) e = run_enhance_bwd<Geo<512, 128, 256>>(a, rows, (cudaStream_t)stream);

@@ -18,10 +18,11 @@ extern "C" int se_enhance_fwd(const float* x, const float* mask, float* y, int64
     if (int rc = get_tables(n_fft, hop, win_length, false, (float)win_length / (float)n_fft, a.ts)) return rc;
     a.x = x; a.mask = mask; a.out = y; a.nsample = (int)nsample; a.nframe = (int)T;
     a.b_lo = (n_fft / 2) / hop; a.b_hi = (int)((n_fft / 2 + nsample + hop - 1) / hop);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop, n_fft >= 2048 ? 1 : 2);
     a.mode = mode; a.pre_tanh = pre_tanh;
     cudaError_t e;
-    SE_DISPATCH_MASK(mode, pre_tanh, SE_DISPATCH_GEO(n_fft, hop, (e = launch(k_enhance_fwd<G, MODE, TANH>,
-        (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ISTFT, (cudaStream_t)stream, a))));
+    SE_DISPATCH_MASK(mode, pre_tanh, SE_DISPATCH_GEO(n_fft, hop, (
+        a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR),
+        e = launch(k_enhance_fwd<G, MODE, TANH>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ISTFT,
+                   (cudaStream_t)stream, a))));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_enhance_fwd launch");
 }

@@ -11,6 +11,14 @@ static const int kRes[3][3] = {{512, 128, 512}, {1024, 256, 1024}, {2048, 512, 2
         else if (n_fft == 1024) { using G = Geo<1024, 256, 256>; CALL; }               \
         else { using G = Geo<2048, 512, 512>; CALL; }                                  \
     } while (0)
+// forward at n = 2048: 8-frame groups halve the working set (64 KB) so that two 256-thread CTAs fit per SM
+#define SE_DISPATCH_LOSS_FWD_GEO(n_fft, CALL)                                          \
+    do {                                                                               \
+        if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                      \
+        else if (n_fft == 1024) { using G = Geo<1024, 256, 256>; CALL; }               \
+        else { using G = Geo<2048, 512, 256, 8>; CALL; }                               \
+    } while (0)
+static int loss_fwd_frames(int n_fft) { return n_fft >= 2048 ? 8 : 16; }
 
 template <class G>
 static cudaError_t run_loss_fwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
@@ -26,7 +34,7 @@ extern "C" {
 // ---------------------------------------------------------------- MR-STFT loss
 static int loss_fwd_plan(int64_t rows, int64_t nsample, int r, int& gpc, int& nchunks) {
     const int64_t T = 1 + nsample / kRes[r][1];
-    plan_analysis(rows, T, gpc, nchunks);
+    plan_analysis(rows, T, gpc, nchunks, loss_fwd_frames(kRes[r][0]));
     return (int)(rows * nchunks);
 }
 
@@ -73,7 +81,7 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
         a.gpc = gpcs[r]; a.nchunks = nchs[r];
         a.chained = r != 2;
         cudaError_t e;
-        SE_DISPATCH_LOSS_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
+        SE_DISPATCH_LOSS_FWD_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd launch");
     }
     // plain stream serialisation: the reduction needs ALL three kernels, not just its immediate predecessor
@@ -110,7 +118,7 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
         a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
         a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
-                              : plan_synthesis(rows, a.b_hi, n / hop, 2);
+                              : plan_synthesis(rows, a.b_hi, n / hop, 2, 16);
         a.accumulate = r != 2;
         a.chained = r != 2;
         a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));

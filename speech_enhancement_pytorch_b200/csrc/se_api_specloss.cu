@@ -11,13 +11,13 @@ static int specloss_args(SpecLossArgs& a, int64_t rows, int64_t nsample, int n_f
     if (kind != 0 && kind != 1) return fail(SE_ERR_UNSUPPORTED, "spectral loss kind must be 0 (mse) or 1 (l1)");
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
     a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop); a.kind = kind;
-    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
+    plan_analysis(rows, a.nframe, a.gpc, a.nchunks, 16);     // every SE_DISPATCH_GEO geometry uses 16-frame groups
     return 0;
 }
 
 extern "C" int64_t se_spectral_loss_workspace_bytes(int64_t rows, int64_t nsample, int hop) {
     int gpc, nchunks;
-    plan_analysis(rows, 1 + nsample / (hop > 0 ? hop : 1), gpc, nchunks);
+    plan_analysis(rows, 1 + nsample / (hop > 0 ? hop : 1), gpc, nchunks, 16);
     return rows * nchunks * (int64_t)sizeof(double);
 }
 

@@ -3,12 +3,15 @@
 
 using namespace se;
 
+// planning happens here, where the geometry (frames per group, CTAs per SM) is known
 template <class G, int LMODE>
-static cudaError_t run_analysis(const AnaArgs& a, int64_t rows, cudaStream_t st) {
+static cudaError_t run_analysis(AnaArgs a, int64_t rows, cudaStream_t st) {
+    plan_analysis(rows, a.nframe, a.gpc, a.nchunks, G::FR);
     return launch(k_analysis<G, LMODE, false>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, st, a);
 }
 template <class G, int EMODE>
-static cudaError_t run_synthesis(const SynArgs& a, int64_t rows, cudaStream_t st) {
+static cudaError_t run_synthesis(SynArgs a, int64_t rows, cudaStream_t st) {
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR);
     return launch(k_synthesis<G, EMODE>, (unsigned)(rows * a.nchunks), G::NT,
                   EMODE == EMIT_ADJ ? Smem<G>::SYNTH_ADJ : Smem<G>::SYNTH_ISTFT, st, a);
 }
@@ -24,7 +27,6 @@ int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int 
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
     a.in = x; a.out = spec; a.in_stride = nsample; a.seg_rows = 1; a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
-    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_fwd launch");
@@ -41,7 +43,6 @@ int se_stft_feature_fwd(const float* x, float* spec, float* feat, int64_t rows, 
     a.in = x; a.out = spec; a.feat = feat; a.feat_kind = kind; a.in_stride = nsample; a.seg_rows = 1;
     a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
-    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_feature_fwd launch");
@@ -71,7 +72,6 @@ int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t ncli
     a.in = x; a.out = spec; a.in_stride = seg_stride; a.clip_stride = clip_stride; a.seg_rows = (int)nclip;
     a.clip_len = (int)clip_len; a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
-    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_segments_fwd launch");
@@ -87,7 +87,6 @@ int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, in
     a.in = gspec; a.out = gx; a.nsample = (int)nsample; a.out_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop);
     a.b_lo = 0; a.b_hi = (int)((nsample + n_fft + hop - 1) / hop);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop, n_fft >= 2048 ? 1 : 2);
     a.accumulate = accumulate; a.edge_scale = 2.0f;
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMIT_ADJ>(a, rows, (cudaStream_t)stream)));
@@ -106,7 +105,6 @@ int se_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int6
     a.in = spec; a.out = y; a.nsample = (int)(n_fft + hop * (nframe - 1)); a.out_len = (int)length;
     a.nframe = (int)nframe;
     a.b_lo = (n_fft / 2) / hop; a.b_hi = (int)((n_fft / 2 + length + hop - 1) / hop);
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, n_fft / hop, n_fft >= 2048 ? 1 : 2);
     a.accumulate = 0; a.edge_scale = 1.0f;
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMIT_ISTFT>(a, rows, (cudaStream_t)stream)));
@@ -122,7 +120,6 @@ int se_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, in
     if (int rc = get_tables(n_fft, hop, win_length, false, scale / (float)n_fft, a.tb)) return rc;
     a.in = gy; a.out = gspec; a.in_stride = length; a.seg_rows = 1; a.in_len = (int)length;
     a.nsample = (int)(n_fft + hop * (nframe - 1)); a.nframe = (int)nframe; a.pad = 0; a.edge_scale = 0.5f;
-    plan_analysis(rows, a.nframe, a.gpc, a.nchunks);
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_ENV>(a, rows, (cudaStream_t)stream)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_istft_bwd launch");

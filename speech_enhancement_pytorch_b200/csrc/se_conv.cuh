@@ -24,6 +24,7 @@ struct ConvArgs {
 };
 
 template <class G> struct ConvGeo {
+    static_assert(G::FR == 16, "the per-frame parity reduction assumes 16 frames per half-warp");
     static constexpr int NOV = 4;                       // ceil(win_len / hop) supported: <= 4
     static constexpr int FROW = G::N + 2 + ((34 - (G::N + 2) % 32) % 32);   // frame row stride == 2 mod 32
     static constexpr int RING = G::FR + NOV - 1;
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* fbuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float2* red = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB + C::FBUF);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + C::FBUF + C::RED, tid);   // visible after the ring-zero barrier below
     pdl_wait();
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
         for (int i = 0; i < G::TA; ++i) {
             const int u = unit + i * G::NU;
 #pragma unroll
-            for (int k = 0; k < G::R1; ++k) v[i][k] = zb[(u + 64 * k) * G::FR + fr];
+            for (int k = 0; k < G::R1; ++k) v[i][k] = zb[zidx<G>(u + 64 * k) + fr];
 #pragma unroll
             for (int k = 1; k < G::R1; ++k) v[i][k] = cmulc(v[i][k], tb.tw[u * k]);
             dftR<G::R1, true>(v[i]);
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float2* red = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB + Smem<G>::STAGE);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE + C::RED, tid);
     pdl_wait();
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
 #pragma unroll
             for (int k = 1; k < G::R1; ++k) v[i][k] = cmul(v[i][k], tb.tw[u * k]);
 #pragma unroll
-            for (int k = 0; k < G::R1; ++k) zb[(u + 64 * k) * G::FR + fr] = v[i][k];
+            for (int k = 0; k < G::R1; ++k) zb[zidx<G>(u + 64 * k) + fr] = v[i][k];
         }
         __syncthreads();
         passB_fwd<G>(tb.tw, zb, unit, fr);

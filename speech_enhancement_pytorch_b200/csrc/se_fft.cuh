@@ -107,12 +107,12 @@ __device__ __forceinline__ void dftR(float2* a) {
 }
 
 // ------------------------------------------------------------------ geometry
-template <int N_, int HOP_, int NT_>
+template <int N_, int HOP_, int NT_, int FR_ = 16>
 struct Geo {
     static constexpr int N = N_, HOP = HOP_, NT = NT_;
     static constexpr int M = N / 2;            // complex points
     static constexpr int R1 = M / 64;          // radix of the time-side pass (4, 8, 16)
-    static constexpr int FR = 16;              // frames per group (= lanes per butterfly)
+    static constexpr int FR = FR_;             // frames per group (= lanes per butterfly): 16, or 8 to halve the working set
     static constexpr int NU = NT / FR;         // butterfly units working in parallel per frame
     static constexpr int MINB = NT <= 256 ? 2 : 1;   // CTAs per SM the register budget is sized for
     static constexpr int TA = 64 / NU;         // pass-A tasks per thread   (64 radix-R1 butterflies)
@@ -120,13 +120,17 @@ struct Geo {
     static constexpr int TC = 4 * R1 / NU;     // pass-C paired tasks per thread (M/16 pairs)
     static constexpr int S = M / 8;            // bin stride between the 8 outputs of a pass-C unit
     static constexpr int F = M + 1;            // one-sided bins
-    // waveform stage: hop-sized rows, padded so that 16 frames (stride HOP) hit distinct banks
-    static constexpr int PADW = (34 - HOP % 32) % 32;
+    // waveform stage: hop-sized rows, padded so that the FR frames x 16/FR units of a half-warp (frame stride
+    // = one row, unit stride = one float2) hit distinct banks: row stride == 2 * (16/FR) words (mod 32)
+    static constexpr int PADW = (32 + 2 * (16 / FR) - HOP % 32) % 32;
     static constexpr int SROW = HOP + PADW;
     static constexpr int SPAN = N + (FR - 1) * HOP;
     static constexpr int SROWS = (SPAN + HOP - 1) / HOP;
     static constexpr int STAGE_FLOATS = SROWS * SROW;
-    static constexpr int ZB_FLOATS = 2 * M * FR;
+    // FR = 8: a half-warp holds two butterflies; in pass C they sit 64 points apart (same banks), so every
+    // 64-point block is shifted by FR float2 against its predecessor
+    static constexpr int ZSKEW = FR < 16 ? FR : 0;
+    static constexpr int ZB_FLOATS = 2 * (M * FR + (M / 64) * ZSKEW);
     // overlap-add (only when HOP divides N)
     static constexpr int OLA = N / HOP;
     static constexpr int SEG = (R1 / OLA) > 0 ? (R1 / OLA) : 1;   // float2 per hop segment per pass-A task
@@ -134,7 +138,12 @@ struct Geo {
     static_assert(NU % 8 == 0, "pass B keeps its twiddles per thread: NU must be a multiple of 8");
     static_assert(TA >= 1 && TB >= 1 && TC >= 1, "too many threads for this size");
     static_assert(HOP % 2 == 0, "hop must be even (float2 staging)");
+    static_assert(FR == 16 || FR == 8, "frames per group");
 };
+
+// float2 index of point p (frame 0) in the working buffer
+template <class G>
+__device__ __forceinline__ int zidx(int p) { return p * G::FR + (p >> 6) * G::ZSKEW; }
 
 // position of pass-C unit q (bins q + S*k4) in zb
 template <class G>
@@ -161,7 +170,7 @@ __device__ __forceinline__ void passA_fwd(const float* __restrict__ stage, const
 #pragma unroll
         for (int k = 1; k < G::R1; ++k) a[k] = cmul(a[k], tw[u * k]);
 #pragma unroll
-        for (int k = 0; k < G::R1; ++k) zb[(u + 64 * k) * G::FR + fr] = a[k];
+        for (int k = 0; k < G::R1; ++k) zb[zidx<G>(u + 64 * k) + fr] = a[k];
     }
 }
 
@@ -174,7 +183,7 @@ __device__ __forceinline__ void passB_fwd(const float2* __restrict__ tw, float2*
 #pragma unroll
     for (int i = 0; i < G::TB; ++i) {
         const int k1 = (unit >> 3) + i * (G::NU / 8);
-        float2* p = zb + (64 * k1 + v) * G::FR + fr;
+        float2* p = zb + zidx<G>(64 * k1 + v) + fr;
         float2 a[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) a[r] = p[8 * r * G::FR];
@@ -189,7 +198,7 @@ __device__ __forceinline__ void passB_fwd(const float2* __restrict__ tw, float2*
 // Pass C for one unit: 8 contiguous points -> Z[q + S*k4], k4 = 0..7 (registers only)
 template <class G>
 __device__ __forceinline__ void passC_fwd_unit(const float2* __restrict__ zb, int q, int fr, float2* z) {
-    const float2* p = zb + unit_base<G>(q) * G::FR + fr;
+    const float2* p = zb + zidx<G>(unit_base<G>(q)) + fr;
 #pragma unroll
     for (int r = 0; r < 8; ++r) z[r] = p[r * G::FR];
     dft8<false>(z);
@@ -260,7 +269,7 @@ __device__ __forceinline__ void merge_task(int p, const float2* __restrict__ twn
 template <class G>
 __device__ __forceinline__ void passC_inv_unit(float2* __restrict__ zb, int q, int fr, float2* z) {
     dft8<true>(z);
-    float2* p = zb + unit_base<G>(q) * G::FR + fr;
+    float2* p = zb + zidx<G>(unit_base<G>(q)) + fr;
 #pragma unroll
     for (int r = 0; r < 8; ++r) p[r * G::FR] = z[r];
 }
@@ -274,7 +283,7 @@ __device__ __forceinline__ void passB_inv(const float2* __restrict__ tw, float2*
 #pragma unroll
     for (int i = 0; i < G::TB; ++i) {
         const int k1 = (unit >> 3) + i * (G::NU / 8);
-        float2* p = zb + (64 * k1 + v) * G::FR + fr;
+        float2* p = zb + zidx<G>(64 * k1 + v) + fr;
         float2 a[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) a[r] = p[8 * r * G::FR];
@@ -291,7 +300,7 @@ template <class G>
 __device__ __forceinline__ void passA_inv_task(const float2* __restrict__ zb, const float* __restrict__ win,
                                                const float2* __restrict__ tw, int u, int fr, float2* a) {
 #pragma unroll
-    for (int k = 0; k < G::R1; ++k) a[k] = zb[(u + 64 * k) * G::FR + fr];
+    for (int k = 0; k < G::R1; ++k) a[k] = zb[zidx<G>(u + 64 * k) + fr];
 #pragma unroll
     for (int k = 1; k < G::R1; ++k) a[k] = cmulc(a[k], tw[u * k]);
     dftR<G::R1, true>(a);
@@ -318,8 +327,8 @@ __device__ __forceinline__ void ola_rotate(const float2* a, int fr, float2* carr
     for (int q = 1; q < G::OLA; ++q) {
 #pragma unroll
         for (int s = 0; s < G::SEG; ++s) {
-            const float rx = __shfl_sync(0xffffffffu, a[q * G::SEG + s].x, (fr - q) & 15, 16);
-            const float ry = __shfl_sync(0xffffffffu, a[q * G::SEG + s].y, (fr - q) & 15, 16);
+            const float rx = __shfl_sync(0xffffffffu, a[q * G::SEG + s].x, (fr - q) & (G::FR - 1), G::FR);
+            const float ry = __shfl_sync(0xffffffffu, a[q * G::SEG + s].y, (fr - q) & (G::FR - 1), G::FR);
             if (fr >= q) { acc[s].x += rx; acc[s].y += ry; }
             else if (CARRY) { nc[s].x += rx; nc[s].y += ry; }
         }

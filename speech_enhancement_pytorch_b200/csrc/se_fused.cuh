@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables ta = stage_tables<G>(a.ta, se_smem + Smem<G>::ZB + Smem<G>::IOBUF, tid);
     const Tables ts = stage_window<G>(ta, a.ts, se_smem + Smem<G>::ZB + Smem<G>::IOBUF + Smem<G>::TABLES, tid);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
     float2* zbx = reinterpret_cast<float2*>(se_smem);
     float2* zbg = reinterpret_cast<float2*>(se_smem + Smem<G>::ZB);
     float* stage = reinterpret_cast<float*>(se_smem + 2 * Smem<G>::ZB);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables ta = stage_tables<G>(a.ta, se_smem + 2 * Smem<G>::ZB + Smem<G>::STAGE, tid);
     const Tables ts = stage_window<G>(ta, a.ts, se_smem + 2 * Smem<G>::ZB + Smem<G>::STAGE + Smem<G>::TABLES, tid);

@@ -136,8 +136,8 @@ static bool envelope_ok_uncached(int n, int hop, int win_len, bool front, int64_
 // ------------------------------------------------------------------ launch planning
 static int g_target_ctas = 148 * 8;
 
-void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks) {
-    const int64_t ng = (T + 15) / 16;
+void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_per_group) {
+    const int64_t ng = (T + frames_per_group - 1) / frames_per_group;
     int64_t g = (rows * ng) / g_target_ctas;
     g = g < 1 ? 1 : (g > 8 ? 8 : g);
     gpc = (int)g;
@@ -146,7 +146,7 @@ void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks) {
 // Pick the groups-per-chunk g that minimises (waves x g): a chunk of g groups emits 16 g - (ola-1)
 // blocks (the first ola-1 frames are halo recompute), so larger g wastes less, but the grid must still
 // fill the GPU in whole waves.  ctas_per_sm = resident CTAs of this kernel per SM.
-int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm) {
+int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group) {
     const int64_t slots = 148LL * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     int best_chunks = 1;
     double best_cost = 1e30;
@@ -154,10 +154,10 @@ int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm) {
     const char* force = std::getenv("SE_FORCE_GROUPS");
     const int g_lo = force ? std::atoi(force) : 1, g_hi = force ? std::atoi(force) : 8;
     for (int g = (g_lo < 1 ? 1 : g_lo); g <= (g_hi > 8 ? 8 : g_hi); ++g) {
-        const int cb_max = 16 * g - (ola - 1);
+        const int cb_max = frames_per_group * g - (ola - 1);
         const int nchunks = (nb + cb_max - 1) / cb_max;
         const int cb = (nb + nchunks - 1) / nchunks;                 // even split (make_chunk)
-        const int groups = (cb + ola - 1 + 15) / 16;
+        const int groups = (cb + ola - 1 + frames_per_group - 1) / frames_per_group;
         const int64_t waves = (rows * nchunks + slots - 1) / slots;
         const double cost = (double)waves * groups;
         if (cost < best_cost - 1e-9) { best_cost = cost; best_chunks = nchunks; }

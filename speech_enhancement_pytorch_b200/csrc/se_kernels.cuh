@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);   // visible after the fill's barrier
     pdl_wait();
@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::OSTAGE);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::OSTAGE + (EMODE == EMIT_ADJ ? Smem<G>::HOLD : 0), tid);
     __syncthreads();
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     __shared__ float red[3][32];
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     // The three resolutions are independent of each other (disjoint outputs): they are launched largest first
     // and chained so that the next one fills the SMs the previous one's last wave leaves idle.  The head of
     // the chain releases its follower only AFTER its own dependencies are met, so followers need not wait.
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* iobuf = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);          // stage, later ostage
     float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::IOBUF);
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     // Chained like the forward kernels (largest first).  Followers accumulate into g_est, which their
     // predecessor writes: they run their whole first group (analysis + synthesis) before waiting, right
     // in front of the first read-modify-write.

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_spec_loss(const SpecLossArgs
     float2* zb = reinterpret_cast<float2*>(se_smem);
     float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
     __shared__ float red[32];
-    const int tid = threadIdx.x, fr = tid & 15, unit = tid >> 4;
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
     pdl_launch_dependents();
     const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);
     pdl_wait();
