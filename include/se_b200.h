@@ -42,11 +42,6 @@ typedef enum se_mask_mode {   /* SURVEY.md 8a row a5 */
     SE_MASK_R = 3             /* re*mr, im*mi        dcunet.py:158-159 dccrn.py:220-221 */
 } se_mask_mode;
 
-typedef enum se_spec_layout {
-    SE_LAYOUT_FT2 = 0,        /* [rows, F, T, 2]  torch.stft real view (src/evaluate.py:109-126) */
-    SE_LAYOUT_PLANAR = 1      /* [rows, 2F, T]    DCCRN conv layout, Re bins then Im bins (dccrn.py:691) */
-} se_spec_layout;
-
 int se_version(void);
 const char* se_last_error(void);
 

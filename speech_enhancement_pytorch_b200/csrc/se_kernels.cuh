@@ -25,12 +25,6 @@ struct Tables {
     const float* inv_env;   // 1 / sum_q w2[o + q*HOP], HOP floats
 };
 
-__device__ __forceinline__ Tables launder_tables(const Tables& t) {
-    Tables r;
-    r.win = launder(t.win); r.tw = launder(t.tw); r.twn = launder(t.twn); r.w2 = launder(t.w2); r.inv_env = launder(t.inv_env);
-    return r;
-}
-
 struct AnaArgs {            // analysis: waveform-like -> spectrum
     Tables tb;
     const float* in;        // [rows, in_len]
@@ -659,19 +653,6 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         const bool live = (t >= 0 && t < a.nframe);
         const int tc = live ? t : 0;
         const float* mrow = a.refmag + (size_t)row * G::F * a.nframe + tc;
-        // |B| is consumed after two passes: start pulling its lines towards L2 now (fr == 0 covers the
-        // 64-byte run of 16 frames; the neighbouring lane group shares the line)
-        if (fr == 0 || fr == 8) {
-#pragma unroll
-            for (int i = 0; i < G::TC; ++i) {
-                const int p = unit + i * G::NU;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    prefetch_l2(mrow + (size_t)(task_qa<G>(p) + G::S * k) * a.nframe);
-                    prefetch_l2(mrow + (size_t)(task_qb<G>(p) + G::S * k) * a.nframe);
-                }
-            }
-        }
         fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
         __syncthreads();
         // |B| for the first task is requested before the passes so its (L2 / DRAM) latency hides behind them;

@@ -22,25 +22,6 @@
 
 namespace se {
 
-// Opaque pointer copy: stops the compiler from hoisting table loads out of a loop (they would
-// otherwise be kept live in registers across whole passes and spill).
-template <class T>
-__device__ __forceinline__ T* launder(T* p) {
-#ifndef SE_EMULATE
-    asm volatile("" : "+l"(p));
-#endif
-    return p;
-}
-
-// L2 prefetch of a line that will be read later in the kernel (no register cost)
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-#ifndef SE_EMULATE
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#else
-    (void)p;
-#endif
-}
-
 // Programmatic dependent launch (sm_90+): every kernel lets its successor start launching as soon
 // as all of its own CTAs are resident, and waits for its predecessors right before it first touches
 // their output.  The successor's prologue (index setup, table staging into shared memory) and its
