@@ -282,7 +282,8 @@ def run_ours(args):
     kernels = []
     if rank == 0 and not args.no_breakdown:
         S_, P_, M_ = 4.0 * N, 8.0 * F * T, 8.0 * F * T
-        R_ = 4.0 * sum((n // 2 + 1) * (1 + N // h) for n, h in RES)     # |B| saved by loss fwd, read by loss bwd
+        # algorithmic bytes per row follow SURVEY.md 8(d): op-boundary traffic, independent of the number of
+        # resolutions (loss fwd 2S, loss bwd 3S); the |B| scratch the two passes exchange is implementation traffic
         flop_fft = lambda n, h: 2.5 * n * (n.bit_length() - 1) * (1 + N // h)
         f1024 = flop_fft(N_FFT, HOP)
         f_all = sum(flop_fft(n, h) for n, h in RES)
@@ -292,8 +293,8 @@ def run_ours(args):
             ("stft_fwd", lambda i: k_stft(sets[i & 1][0]), S_ + P_, f1024, 1),
             ("mask_fwd", lambda i: k_mask(sets[i & 1][2]), 2 * P_ + M_, 0, 1),
             ("istft_fwd", lambda i: k_istft(), P_ + S_, f1024, 1),
-            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 4),
-            ("mrstft_loss_bwd(3 res)", lambda i: k_loss_bwd(sets[i & 1][1]), 3 * 2 * S_ + R_, 2 * f_all, 3),
+            ("mrstft_loss_fwd(3 res)", lambda i: k_loss_fwd(sets[i & 1][1]), 2 * S_, 2 * f_all, 4),
+            ("mrstft_loss_bwd(3 res)", lambda i: k_loss_bwd(sets[i & 1][1]), 3 * S_, 2 * f_all, 3),
             ("istft_bwd", lambda i: k_istft_bwd(), S_ + P_, f1024, 1),
             ("mask_bwd", lambda i: k_mask_bwd(sets[i & 1][2]), 2 * P_ + 2 * M_, 0, 1),
         ]
@@ -414,7 +415,8 @@ def run_ours(args):
                     "share_of_step": round(dom["us"] / sum(k["us"] for k in in_step), 3),
                     "fp32": {"achieved_tflops": dom["tflops_fp32"], "peak_tflops": round(fp32_peak, 1),
                              "frac": round(dom["tflops_fp32"] / fp32_peak, 4),
-                             "note": "MR-STFT loss is fp32-pipe bound (~75 flop/B, SURVEY 8d); flops = 2.5 n log2 n per frame"}}
+                             "note": "MR-STFT loss is fp32-pipe bound (~75 flop/B against an fp32 ridge of 11.4 flop/B, SURVEY 8d): "
+                                     "the HBM fraction of this kernel cannot be high; flops = 2.5 n log2 n per transform actually run"}}
         for k in kernels:
             k["hbm_frac"] = round(k["gbs"] / hbm_peak, 4)
 
