@@ -160,13 +160,20 @@ def stream_ptr(device) -> int:
 
 
 class on_device:
-    """Make `device` current around a C-ABI call (tables are cached per current device)."""
+    """Make `device` current around a C-ABI call (tables are cached per current device).  A no-op when it
+    already is -- the common single-GPU-per-process case -- because the guard costs several microseconds."""
+
+    __slots__ = ("guard",)
 
     def __init__(self, device):
-        self.guard = torch.cuda.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self.guard = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
 
     def __enter__(self):
-        self.guard.__enter__()
+        if self.guard is not None:
+            self.guard.__enter__()
 
     def __exit__(self, *a):
-        return self.guard.__exit__(*a)
+        if self.guard is not None:
+            return self.guard.__exit__(*a)
+        return False

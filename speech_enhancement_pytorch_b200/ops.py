@@ -95,14 +95,24 @@ def _as_f32(t):
     return t
 
 
+def _needs_grad(*tensors):
+    return torch.is_grad_enabled() and any(t.requires_grad for t in tensors)
+
+
 def stft(x_rows, n_fft, hop, win_length, scale):
     _check_cfg(n_fft, hop, win_length)
-    return _STFT.apply(_as_f32(x_rows).contiguous(), n_fft, hop, win_length, float(scale))
+    x = _as_f32(x_rows).contiguous()
+    if not _needs_grad(x):                      # inference / no-grad inputs: skip the autograd node
+        return stft_rows(x, n_fft, hop, win_length, float(scale))
+    return _STFT.apply(x, n_fft, hop, win_length, float(scale))
 
 
 def istft(spec_rows, length, n_fft, hop, win_length, scale):
     _check_cfg(n_fft, hop, win_length)
-    return _ISTFT.apply(_as_f32(spec_rows).contiguous(), int(length), n_fft, hop, win_length, float(scale))
+    spec = _as_f32(spec_rows).contiguous()
+    if not _needs_grad(spec):
+        return istft_rows(spec, int(length), n_fft, hop, win_length, float(scale))
+    return _ISTFT.apply(spec, int(length), n_fft, hop, win_length, float(scale))
 
 
 class _Mask(torch.autograd.Function):
