@@ -127,6 +127,16 @@ int se_spectral_loss_bwd(const float* enh, const float* target, const float* gou
                          int64_t nsample, int n_fft, int hop, int win_length, float scale, int kind, float* genh,
                          void* stream);
 
+/* ---- phase-sensitive spectral approximation, loss_phase_sensitive_spectral_approximation(enhance,
+ * target, mixture), src/loss.py:32-56 (the `psa` key of src/distrib.py:271-272): three spectra [count,2].
+ * fwd -> *sum_out (device double) = sum of squared residuals (mean = sum / global_count; all-reduce first
+ * when sharded); bwd: genh [count,2] = gout * d mean / d enhance. */
+int64_t se_psa_workspace_bytes(int64_t count);
+int se_psa_loss_fwd(const float* enh, const float* tgt, const float* mix, int64_t count, double* sum_out,
+                    void* workspace, void* stream);
+int se_psa_loss_bwd(const float* enh, const float* tgt, const float* mix, const float* gout, int64_t global_count,
+                    int64_t count, float* genh, void* stream);
+
 /* ---- time-domain SI-SNR: si_snr(s1, s2, eps=1e-8) / loss_sisdr, src/loss.py:14-29.
  * fwd: s1, s2 [rows,N] -> dots [rows,3] (device double: <s1,s1>, <s1,s2>, <s2,s2>) and snr [rows]
  * (10 log10(|s_target|^2 / (|e|^2 + eps) + eps)); the caller takes the mean (and the sign for loss_sisdr).

@@ -306,3 +306,13 @@ def si_snr_ref(s1, s2, eps=1e-8):
     tn = torch.sum(s_target * s_target, -1, keepdim=True)
     nn_ = torch.sum(e_noise * e_noise, -1, keepdim=True)
     return torch.mean(10 * torch.log10(tn / (nn_ + eps) + eps))
+
+
+def psa_loss_ref(enhance, target, mixture):
+    """src/loss.py:32-56 (eps 1e-9; the angles are tanh of the tangent, as written there)."""
+    eps = 1e-9
+    a_mix = torch.tanh(mixture[..., 1] / (mixture[..., 0] + eps))
+    a_tgt = torch.tanh(target[..., 1] / (target[..., 0] + eps))
+    amp_e = torch.sqrt(enhance[..., 1] ** 2 + enhance[..., 0] ** 2)
+    amp_t = torch.sqrt(target[..., 1] ** 2 + target[..., 0] ** 2)
+    return torch.mean((amp_e - amp_t * torch.cos(a_tgt - a_mix)) ** 2)

@@ -15,11 +15,12 @@ Public surface (all CUDA-only, no CPU fallback):
 """
 from .evaluate import stft_custom, istft_custom, stft_custom_with_feature, evaluate, segment_stft, stitch_segments
 from .masking import apply_mask, apply_mask_dccrn, magnitude_feature
-from .loss import loss_mrstft, MRSTFTLoss, loss_spectral, si_snr, loss_sisdr
+from .loss import (loss_mrstft, MRSTFTLoss, loss_spectral, si_snr, loss_sisdr,
+                   loss_phase_sensitive_spectral_approximation)
 from .dccrn import ConvSTFT, ConviSTFT
 from .fused import enhance
 from . import _native
 
-__all__ = ["stft_custom", "istft_custom", "stft_custom_with_feature", "magnitude_feature", "evaluate", "segment_stft", "stitch_segments", "apply_mask", "apply_mask_dccrn", "loss_mrstft", "MRSTFTLoss", "loss_spectral", "si_snr", "loss_sisdr",
+__all__ = ["stft_custom", "istft_custom", "stft_custom_with_feature", "magnitude_feature", "evaluate", "segment_stft", "stitch_segments", "apply_mask", "apply_mask_dccrn", "loss_mrstft", "MRSTFTLoss", "loss_spectral", "si_snr", "loss_sisdr", "loss_phase_sensitive_spectral_approximation",
            "ConvSTFT", "ConviSTFT", "enhance"]
 __version__ = "0.1.0"

@@ -23,7 +23,7 @@ EXPORTS = (
     "se_version", "se_last_error", "se_stft_fwd", "se_stft_segments_fwd", "se_magnitude_feature", "se_stft_feature_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
     "se_mask_fwd", "se_mask_bwd", "se_mrstft_workspace_bytes", "se_mrstft_loss_fwd",
     "se_mrstft_loss_value", "se_mrstft_loss_bwd", "se_spectral_loss_workspace_bytes", "se_spectral_loss_fwd",
-    "se_spectral_loss_bwd", "se_sisnr_fwd", "se_sisnr_bwd", "se_enhance_fwd", "se_enhance_bwd",
+    "se_spectral_loss_bwd", "se_sisnr_fwd", "se_sisnr_bwd", "se_psa_workspace_bytes", "se_psa_loss_fwd", "se_psa_loss_bwd", "se_enhance_fwd", "se_enhance_bwd",
     "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
 )
 
@@ -120,6 +120,10 @@ def lib():
             L.se_spectral_loss_bwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _PTR, _PTR]
             L.se_sisnr_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _c.c_double, _PTR, _PTR, _PTR]
             L.se_sisnr_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _F32, _I64, _I64, _c.c_double, _PTR, _PTR]
+            L.se_psa_workspace_bytes.restype = _I64
+            L.se_psa_workspace_bytes.argtypes = [_I64]
+            L.se_psa_loss_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _PTR, _PTR, _PTR]
+            L.se_psa_loss_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _PTR, _PTR]
             L.se_enhance_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
             L.se_enhance_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
             L.se_conv_stft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _PTR]

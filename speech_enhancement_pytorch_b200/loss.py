@@ -65,3 +65,10 @@ def si_snr(s1, s2, eps=1e-8):
 def loss_sisdr(inputs, targets):
     """`loss_sisdr` of src/loss.py:14-15."""
     return -si_snr(inputs, targets)
+
+
+def loss_phase_sensitive_spectral_approximation(enhance, target, mixture, group=None):
+    """`loss_phase_sensitive_spectral_approximation(enhance, target, mixture)` of src/loss.py:32-56 (the
+    `psa` loss, src/distrib.py:271-272; called with the mixture as third argument, src/solver.py:477-480),
+    one fused elementwise-and-reduce pass over the three spectra [...,F,T,2]."""
+    return ops.psa_loss(enhance, target, mixture, group)

@@ -269,6 +269,45 @@ def si_snr_rows(s1_rows, s2_rows, eps=1e-8):
     return _SiSnr.apply(_as_f32(s1_rows).contiguous(), _as_f32(s2_rows).contiguous(), eps)
 
 
+class _PSA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enh, tgt, mix, group):
+        nv.require_cuda_f32(enh, tgt, mix)
+        count = enh.numel() // 2
+        L = nv.lib()
+        ws = torch.empty(max(int(L.se_psa_workspace_bytes(count)), 8), dtype=torch.uint8, device=enh.device)
+        total = torch.empty((), dtype=torch.float64, device=enh.device)
+        with nv.on_device(enh.device):
+            nv.check(L.se_psa_loss_fwd(enh.data_ptr(), tgt.data_ptr(), mix.data_ptr(), count, total.data_ptr(), ws.data_ptr(),
+                                       nv.stream_ptr(enh.device)))
+        global_count = count
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(total, group=group)
+            global_count = count * dist.get_world_size(group)
+        ctx.save_for_backward(enh, tgt, mix)
+        ctx.global_count = global_count
+        return (total / global_count).float()
+
+    @staticmethod
+    def backward(ctx, gout):
+        enh, tgt, mix = ctx.saved_tensors
+        g = torch.empty_like(enh)
+        gout = gout.contiguous().float()
+        with nv.on_device(enh.device):
+            nv.check(nv.lib().se_psa_loss_bwd(enh.data_ptr(), tgt.data_ptr(), mix.data_ptr(), gout.data_ptr(), ctx.global_count,
+                                              enh.numel() // 2, g.data_ptr(), nv.stream_ptr(enh.device)))
+        return g, None, None, None
+
+
+def psa_loss(enh, tgt, mix, group=None):
+    if tgt.requires_grad or mix.requires_grad:
+        raise NotImplementedError("psa loss: gradient flows to `enhance` only")
+    if enh.shape != tgt.shape or enh.shape != mix.shape or enh.shape[-1] != 2:
+        raise ValueError("psa loss expects three spectra of identical shape [...,2]")
+    return _PSA.apply(_as_f32(enh).contiguous(), _as_f32(tgt).contiguous(), _as_f32(mix).contiguous(), group)
+
+
 # ------------------------------------------------------------------ fused enhance
 class _Enhance(torch.autograd.Function):
     @staticmethod

@@ -541,3 +541,20 @@ def test_cuda_graph_capture_and_replay(se):
         want = se.istft_custom(se.apply_mask(se.stft_custom(x, c), raw, "E", True), 16000, c)
     assert float((y - want).abs().max()) == 0.0
     assert float((y2 - want).abs().max()) < 1e-5
+
+
+def test_psa_loss_and_gradient(se, oref):
+    """src/loss.py:32-56, the `psa` training loss (src/distrib.py:271-272)."""
+    g = torch.Generator().manual_seed(4)
+    shape = (3, 1, 257, 40, 2)
+    enh, tgt, mix = (torch.randn(*shape, generator=g) for _ in range(3))
+    er = enh.double().requires_grad_(True)
+    want = oref.psa_loss_ref(er, tgt.double(), mix.double())
+    (gw,) = torch.autograd.grad(want, er)
+    ec = enh.cuda().requires_grad_(True)
+    got = se.loss_phase_sensitive_spectral_approximation(ec, tgt.cuda(), mix.cuda())
+    assert got.dim() == 0
+    assert abs(float(got) - float(want)) / float(want) < 1e-4
+    (gg,) = torch.autograd.grad(got, ec)
+    assert rel(gg, gw) < TOL_GRAD
+    assert abs(float(got) - float(oref.psa_loss_ref(enh, tgt, mix))) / float(want) < 1e-4
