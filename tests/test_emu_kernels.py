@@ -242,3 +242,27 @@ def test_emu_fused_spectral_loss(kind, fn):
     else:                                   # sign() flips only where |e - s| is at round-off level
         same = np.sign(g) == np.sign(gw.numpy())
         assert same.mean() > 0.999
+
+
+@pytest.mark.parametrize("n,hop", [(512, 128), (512, 256), (1024, 256)])
+def test_emu_edge_lengths(n, hop):
+    """Lengths around every seam: the reflect limit (N = n/2+1), N = n, hop multiples +-1, and the
+    13/16-block chunk boundaries; iSTFT with shorter / longer `length`; all four transforms."""
+    rng = np.random.default_rng(n + hop)
+    F = n // 2 + 1
+    for N in (n // 2 + 1, n - 1, n, n + hop - 1, 13 * hop, 13 * hop + 1, 16 * hop - 1, 16 * hop + 1, 29 * hop + 5):
+        x = rng.standard_normal((1, N)).astype(np.float32)
+        T = 1 + N // hop
+        assert rel(c2(E.stft_fwd(x, n, hop, n, 1.0 / n)), o64.stft(x, n, hop, n)) < 2e-6, N
+        spec = rng.standard_normal((1, F, T)) + 1j * rng.standard_normal((1, F, T))
+        for length in (N, max(1, N - 77), N + 50):
+            y = E.istft_fwd(r2(spec), length, n, hop, n, float(n))
+            assert not np.isnan(y).any(), (N, length)
+            assert rel(y, o64.istft(spec.astype(np.complex64), n, hop, n, length)) < 5e-6, (N, length)
+            gy = rng.standard_normal((1, length)).astype(np.float32)
+            gs = E.istft_bwd(gy, T, n, hop, n, float(n))
+            assert rel(c2(gs), o64.istft_adjoint(gy, T, n, hop, n)) < 5e-6, (N, length)
+        if N >= n:
+            gx = E.stft_bwd(r2(spec), N, n, hop, n, 1.0 / n)
+            assert not np.isnan(gx).any(), N
+            assert rel(gx, o64.stft_adjoint(c2(r2(spec)), N, n, hop, n)) < 5e-6, N
