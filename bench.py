@@ -40,7 +40,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the per-kernel timing loops (for ncu runs)")
-    ap.add_argument("--fused", type=int, default=-1, help="1: fused enhance kernels, 0: unfused, -1: auto")
+    ap.add_argument("--fused", type=int, default=-1,
+                    help="composition: 2 (default, -1): stft_custom + apply_mask_istft (tail fused with the iSTFT); "
+                         "0: five drop-in kernels; 1: se.enhance (everything fused, STFT recomputed in backward)")
     return ap.parse_args()
 
 
@@ -178,10 +180,12 @@ def run_ours(args):
     L = nv.lib()
     rows, N = args.rows, args.nsample
     F, T = N_FFT // 2 + 1, 1 + N // HOP
-    # default: the drop-in ops (stft_custom / apply_mask / istft_custom); --fused 1 = se.enhance kernels.
-    # At this batch the 66 MB spectra stay in the 126 MB L2 between kernels, so the unfused chain is
-    # currently the faster composition; both are timed and reported.
-    use_fused = args.fused == 1
+    # three compositions of the same step, all timed and reported; the first is the default:
+    #   "tail"   stft_custom, then apply_mask_istft (mask tail + iSTFT in one launch each way; the masked
+    #            spectrum and its gradient are never written) -- 3 launches around the loss
+    #   "dropin" stft_custom / apply_mask / istft_custom one kernel each -- 5 launches
+    #   "fused"  se.enhance: everything in one launch each way (the backward recomputes the STFT) -- 2 launches
+    comp = {0: "dropin", 1: "fused"}.get(args.fused, "tail")
 
     # ---- device-resident inputs (2 rotating sets) and preallocated intermediates
     g = torch.Generator(device="cpu").manual_seed(1235 + rank)
@@ -216,11 +220,15 @@ def run_ours(args):
     def k_mask_bwd(raw): nv.check(L.se_mask_bwd(P(X), P(raw), P(gY), P(graw), 0, count, 1, 1, st))
     def k_enh_fwd(x, raw): nv.check(L.se_enhance_fwd(P(x), P(raw), P(y), rows, N, N_FFT, HOP, WIN, 1, 1, st))
     def k_enh_bwd(x, raw): nv.check(L.se_enhance_bwd(P(gy), P(x), P(raw), P(graw), rows, N, N_FFT, HOP, WIN, 1, 1, st))
+    def k_tail_fwd(raw): nv.check(L.se_mask_istft_fwd(P(X), P(raw), P(y), rows, T, N, N_FFT, HOP, WIN, float(WIN), 1, 1, st))
+    def k_tail_bwd(raw): nv.check(L.se_mask_istft_bwd(P(gy), P(X), P(raw), P(graw), rows, T, N, N_FFT, HOP, WIN, float(WIN), 1, 1, st))
 
-    def step(i, use_fused=use_fused):
+    def step(i, comp=comp):
         x, clean, raw = sets[i & 1]
-        if use_fused:
+        if comp == "fused":
             k_enh_fwd(x, raw)
+        elif comp == "tail":
+            k_stft(x); k_tail_fwd(raw)
         else:
             k_stft(x); k_mask(raw); k_istft()
         k_loss_fwd(clean)
@@ -228,12 +236,14 @@ def run_ours(args):
             dist.all_reduce(sums, group=group)          # the path's only exchange step
         k_loss_val()
         k_loss_bwd(clean)
-        if use_fused:
+        if comp == "fused":
             k_enh_bwd(x, raw)
+        elif comp == "tail":
+            k_tail_bwd(raw)
         else:
             k_istft_bwd(); k_mask_bwd(raw)
 
-    n_launch = (2 if use_fused else 5) + 4 + 1 + 3      # + 3 loss fwd, 1 reduce, value, 3 loss bwd
+    n_launch = {"fused": 2, "tail": 3, "dropin": 5}[comp] + 4 + 1 + 3      # + 3 loss fwd, 1 reduce, value, 3 loss bwd
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -260,20 +270,25 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms)
     ms_per_step = total_ms / args.steps
-    # the other composition (fused <-> unfused drop-in ops), same timing rules, for context
-    for i in range(3):
-        step(i, not use_fused)
-    sync_all()
-    e0.record()
-    for i in range(args.steps):
-        step(i, not use_fused)
-    e1.record()
-    sync_all()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if group is not None:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    alt_ms = float(ms2) / args.steps
+    # the other compositions, same timing rules, for context
     audio_s = rows * world * N / SR
+    alts = []
+    for other in ("tail", "dropin", "fused"):
+        if other == comp:
+            continue
+        for i in range(3):
+            step(i, other)
+        sync_all()
+        e0.record()
+        for i in range(args.steps):
+            step(i, other)
+        e1.record()
+        sync_all()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if group is not None:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        alt_ms = float(ms2) / args.steps
+        alts.append({"composition": other, "ms_per_step": alt_ms, "value": audio_s / (alt_ms * 1e-3)})
     value = audio_s / (ms_per_step * 1e-3)
     loss_val = float(loss)
 
@@ -289,6 +304,8 @@ def run_ours(args):
         table = [
             ("enhance_fwd", lambda i: k_enh_fwd(sets[i & 1][0], sets[i & 1][2]), 2 * S_ + M_, 2 * f1024, 1),
             ("enhance_bwd", lambda i: k_enh_bwd(sets[i & 1][0], sets[i & 1][2]), 2 * S_ + 2 * M_, 2 * f1024, 1),
+            ("mask_istft_fwd", lambda i: k_tail_fwd(sets[i & 1][2]), P_ + M_ + S_, f1024, 1),
+            ("mask_istft_bwd", lambda i: k_tail_bwd(sets[i & 1][2]), S_ + P_ + 2 * M_, f1024, 1),
             ("stft_fwd", lambda i: k_stft(sets[i & 1][0]), S_ + P_, f1024, 1),
             ("mask_fwd", lambda i: k_mask(sets[i & 1][2]), 2 * P_ + M_, 0, 1),
             ("istft_fwd", lambda i: k_istft(), P_ + S_, f1024, 1),
@@ -346,8 +363,10 @@ def run_ours(args):
             main.wait_event(ready[j])
             x, clean = dbuf[j][0], dbuf[j][1]
             raw = dbuf[j][2].detach().requires_grad_(True)
-            if use_fused:
+            if comp == "fused":
                 yy = se.enhance(x, raw, cfg, "E", True)
+            elif comp == "tail":
+                yy = se.apply_mask_istft(se.stft_custom(x, cfg), raw, N, cfg, "E", True)
             else:
                 yy = se.istft_custom(se.apply_mask(se.stft_custom(x, cfg), raw, "E", True), N, cfg)
             l = se.loss_mrstft(yy, clean, group)
@@ -382,7 +401,8 @@ def run_ours(args):
                "h2d_gbs": round(h2d / (e2e_ms * 1e-3) * 1e-9, 1),
                "note": "copy-bound: the 98.7 MB/step of pinned-host inputs (mixture, clean, raw mask) saturate PCIe; "
                        "kernels overlap underneath on the compute stream",
-               "api": "stft_custom/apply_mask/istft_custom/loss_mrstft + autograd; pinned host inputs, copy stream double-buffered",
+               "api": {"tail": "stft_custom/apply_mask_istft", "dropin": "stft_custom/apply_mask/istft_custom",
+                       "fused": "enhance"}[comp] + "/loss_mrstft + autograd; pinned host inputs, copy stream double-buffered",
                "loss": float(hloss)}
 
     if rank != 0:
@@ -398,8 +418,9 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    fused_names = ("enhance_fwd", "enhance_bwd")
-    in_step = [k for k in kernels if k["name"].startswith("mrstft") or (k["name"] in fused_names) == use_fused]
+    members = {"fused": ("enhance_fwd", "enhance_bwd"), "tail": ("stft_fwd", "mask_istft_fwd", "mask_istft_bwd"),
+               "dropin": ("stft_fwd", "mask_fwd", "istft_fwd", "istft_bwd", "mask_bwd")}[comp]
+    in_step = [k for k in kernels if k["name"].startswith("mrstft") or k["name"] in members]
     dom = max(in_step, key=lambda k: k["us"]) if in_step else None
     traffic = None
     try:
@@ -437,8 +458,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
-        "fused": use_fused, "alt_composition": {"fused": not use_fused, "ms_per_step": alt_ms,
-                                                "value": audio_s / (alt_ms * 1e-3)},
+        "composition": comp, "alt_compositions": alts,
         "loss": loss_val, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))
     if group is not None:

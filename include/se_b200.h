@@ -155,6 +155,19 @@ int se_enhance_fwd(const float* x, const float* mask, float* y, int64_t rows, in
 int se_enhance_bwd(const float* gy, const float* x, const float* mask, float* gmask, int64_t rows,
                    int64_t nsample, int n_fft, int hop, int win_length, int mode, int pre_tanh, void* stream);
 
+/* ---- model tail + iSTFT in one launch: y = istft_custom(apply_mask(spec, mask), length)
+ * (the mask tails listed at se_mask_fwd followed by src/evaluate.py:130-153 as evaluate() and
+ * Solver._run_one_epoch chain them, src/evaluate.py:54-72, src/solver.py:466-480) without writing the
+ * masked spectrum.  spec [rows,F,T,2], mask [rows,F,T] (REAL) or [rows,F,T,2], y [rows,length];
+ * scale as se_istft_fwd (win_length).  bwd: gy [rows,length] -> gmask (gradient wrt the raw mask;
+ * spec is treated as a constant, as it is when it comes from stft_custom(mixture)). */
+int se_mask_istft_fwd(const float* spec, const float* mask, float* y, int64_t rows, int64_t nframe,
+                      int64_t length, int n_fft, int hop, int win_length, float scale, int mode, int pre_tanh,
+                      void* stream);
+int se_mask_istft_bwd(const float* gy, const float* spec, const float* mask, float* gmask, int64_t rows,
+                      int64_t nframe, int64_t length, int n_fft, int hop, int win_length, float scale, int mode,
+                      int pre_tanh, void* stream);
+
 /* ---- DCCRN in-model transforms: ConvSTFT.forward / ConviSTFT.forward, src/model/dccrn.py:687-747
  * x [rows,N] -> spec [rows, 2F, T], T = (N + 2(win_len-win_inc) - win_len)/win_inc + 1, Hann
  * window, zero padding, frame zero-extended at the END to fft_len.  Supported: fft_len 512,

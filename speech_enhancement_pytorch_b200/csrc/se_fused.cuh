@@ -156,3 +156,153 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
 }
 
 }  // namespace se
+
+// ------------------------------------------------------------------------------------------------------
+// Model tail + iSTFT in one kernel: istft_custom(apply_mask(spec, mask)) -- what the reference does at the end
+// of every STFT model's forward followed by src/evaluate.py:72 / src/model/dccrn.py:223-224 -- without writing
+// the masked spectrum, and its backward (gy -> d/d raw mask) without writing d/d masked spectrum.  One working
+// buffer, so two CTAs per SM like the plain transforms (the fully fused se_enhance_bwd needs two).
+namespace se {
+
+struct MaskSynArgs {
+    Tables ts;               // window * win_length / n (env tables valid)
+    const float* spec;       // [rows, F, T, 2]
+    const float* mask;       // [rows, F, T] or [rows, F, T, 2]
+    const float* gy;         // bwd: [rows, length]
+    float* out;              // fwd: y [rows, length]; bwd: gmask
+    int nframe, length, natural;
+    int b_lo, b_hi, nchunks; // fwd
+    int gpc;                 // bwd
+};
+
+template <class G, int MODE>
+__device__ __forceinline__ float2 load_mask_at(const float* __restrict__ mask, size_t idx) {
+    if (MODE == 0) return make_float2(__ldg(mask + idx), 0.f);
+    return __ldg(reinterpret_cast<const float2*>(mask) + idx);
+}
+
+template <class G, int MODE, bool TANH>
+__global__ void __launch_bounds__(G::NT, G::MINB) k_mask_istft_fwd(const MaskSynArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
+    pdl_launch_dependents();
+    const Tables tb = stage_tables<G>(a.ts, se_smem + Smem<G>::ZB + Smem<G>::OSTAGE, tid);
+    __syncthreads();
+    pdl_wait();
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
+    SynArgs sa;
+    sa.tb = a.ts; sa.nsample = a.natural; sa.out_len = a.length; sa.nframe = a.nframe;
+    const size_t rbase = (size_t)row * G::F * a.nframe;
+    const float2* spec = reinterpret_cast<const float2*>(a.spec) + rbase;
+    float* out_row = a.out + (size_t)row * a.length;
+    float2 carry[G::TA][G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i)
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
+    for (int g = 0; g < c.ngroups; ++g) {
+        const int f_base = c.f0 + g * G::FR;
+        const int t = f_base + fr;
+        const bool live = (t >= 0 && t < a.nframe);
+        const int tc = live ? t : 0;                       // clamped: loads stay in bounds, result zeroed
+        SE_TC_PRAGMA
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+            float2 ya[8], yb[8], nyq;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const size_t ia = (size_t)(qa + G::S * k) * a.nframe + tc, ib = (size_t)(qb + G::S * k) * a.nframe + tc;
+                ya[k] = MaskMath::apply<MODE, TANH>(__ldg(spec + ia), load_mask_at<G, MODE>(a.mask, rbase + ia));
+                yb[k] = MaskMath::apply<MODE, TANH>(__ldg(spec + ib), load_mask_at<G, MODE>(a.mask, rbase + ib));
+                if (!live) ya[k] = yb[k] = make_float2(0.f, 0.f);
+            }
+            nyq = make_float2(0.f, 0.f);
+            if (p == 0 && live) {
+                const size_t in = (size_t)G::M * a.nframe + tc;
+                nyq = MaskMath::apply<MODE, TANH>(__ldg(spec + in), load_mask_at<G, MODE>(a.mask, rbase + in));
+            }
+            synthesis_task<G>(zb, tb, p, fr, ya, yb, nyq);
+        }
+        synthesis_tail<G>(zb, tb, ostage, unit, fr, carry);
+        emit_istft<G>(ostage, out_row, f_base, c, sa, tid);
+    }
+}
+
+template <class G, int MODE, bool TANH>
+__device__ __forceinline__ void mask_grad_half(const MaskSynArgs& a, const float2* x, const float2* m, const float2* gy,
+                                               size_t rbase, int q, int t, bool edge) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float2 g = gy[k];
+        // iSTFT adjoint: c_k / n with the 2/n folded into the window -> DC gets 1/2, real part only
+        if (k == 0 && edge) g = make_float2(0.5f * g.x, 0.f);
+        float2 gm, gx;
+        MaskMath::grad<MODE, TANH>(x[k], m[k], g, gm, gx);
+        const size_t idx = rbase + (size_t)(q + G::S * k) * a.nframe + t;
+        if (MODE == 0) a.out[idx] = gm.x;
+        else reinterpret_cast<float2*>(a.out)[idx] = gm;
+    }
+}
+
+template <class G, int MODE, bool TANH>
+__global__ void __launch_bounds__(G::NT, G::MINB) k_mask_istft_bwd(const MaskSynArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* stage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
+    pdl_launch_dependents();
+    const Tables tb = stage_tables<G>(a.ts, se_smem + Smem<G>::ZB + Smem<G>::STAGE, tid);
+    pdl_wait();
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    AnaArgs lg;
+    lg.tb = a.ts; lg.nsample = a.natural; lg.nframe = a.nframe; lg.in_len = a.length; lg.pad = 0;
+    const size_t rbase = (size_t)row * G::F * a.nframe;
+    const float2* spec = reinterpret_cast<const float2*>(a.spec) + rbase;
+    for (int g = 0; g < a.gpc; ++g) {
+        const int f_base = (chunk * a.gpc + g) * G::FR;
+        if (f_base >= a.nframe) break;
+        const int t = f_base + fr;
+        const bool live = t < a.nframe;
+        const int tc = live ? t : 0;                       // clamped: loads stay in bounds, nothing stored
+        fill_stage<G, LOAD_ENV>(stage, a.gy + (size_t)row * a.length, f_base * G::HOP, lg, tid);
+        __syncthreads();
+        analysis_passes<G>(stage, tb, zb, unit, fr);
+        SE_TC_PRAGMA
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+            float2 x[8], m[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                  // unit a's operands in flight while pass C runs
+                const size_t idx = (size_t)(qa + G::S * k) * a.nframe + tc;
+                x[k] = __ldg(spec + idx);
+                m[k] = load_mask_at<G, MODE>(a.mask, rbase + idx);
+            }
+            float2 ga[8], gb[8], gn;
+            analysis_task<G>(zb, tb, p, fr, ga, gb, gn);
+            if (live) mask_grad_half<G, MODE, TANH>(a, x, m, ga, rbase, qa, t, p == 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const size_t idx = (size_t)(qb + G::S * k) * a.nframe + tc;
+                x[k] = __ldg(spec + idx);
+                m[k] = load_mask_at<G, MODE>(a.mask, rbase + idx);
+            }
+            if (live) mask_grad_half<G, MODE, TANH>(a, x, m, gb, rbase, qb, t, false);
+            if (p == 0 && live) {                          // Nyquist
+                const size_t idx = (size_t)G::M * a.nframe + t;
+                float2 gm, gx;
+                MaskMath::grad<MODE, TANH>(__ldg(spec + idx), load_mask_at<G, MODE>(a.mask, rbase + idx),
+                                           make_float2(0.5f * gn.x, 0.f), gm, gx);
+                if (MODE == 0) a.out[rbase + idx] = gm.x;
+                else reinterpret_cast<float2*>(a.out)[rbase + idx] = gm;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace se

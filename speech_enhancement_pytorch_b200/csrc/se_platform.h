@@ -9,9 +9,11 @@
 #ifdef SE_EMULATE
 #include "cuda_emu.h"
 #define SE_SMEM_DECL unsigned char* se_smem = emu::g_dyn_smem
+#define SE_NOINLINE __attribute__((noinline))
 #else
 #include <cuda_runtime.h>
 #define SE_SMEM_DECL extern __shared__ __align__(16) unsigned char se_smem[]
+#define SE_NOINLINE __noinline__
 #endif
 
 #include <cstddef>
@@ -34,6 +36,38 @@ __device__ __forceinline__ void pdl_launch_dependents() {
 __device__ __forceinline__ void pdl_wait() {
 #ifndef SE_EMULATE
     asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+// Single-instruction MUFU forms (rsqrt / rcp / lg2 .approx.ftz).  The CUDA intrinsics rsqrtf, __fdividef and
+// __log2f wrap the same MUFU in denormal/range fix-ups (a compare and two predicated multiplies each); every call
+// site here passes a clamped, normal-range argument, so the per-bin math drops those instructions.  Denormal
+// inputs are flushed to zero (rsqrt, rcp -> inf; lg2 -> -inf): callers guard with fmaxf / select.
+__device__ __forceinline__ float se_rsqrt(float x) {
+#ifdef SE_EMULATE
+    return 1.0f / sqrtf(x);
+#else
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float se_rcp(float x) {
+#ifdef SE_EMULATE
+    return 1.0f / x;
+#else
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#endif
+}
+__device__ __forceinline__ float se_log2(float x) {
+#ifdef SE_EMULATE
+    return log2f(x);
+#else
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 #endif
 }
 

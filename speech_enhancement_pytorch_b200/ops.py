@@ -353,6 +353,48 @@ def enhance_rows(x_rows, mask_rows, n_fft, hop, win_length, mode, pre_tanh=False
                           nv.MASK_MODES[mode], bool(pre_tanh))
 
 
+class _MaskISTFT(torch.autograd.Function):
+    """istft_custom(apply_mask(spec, mask)) in one launch each way; the masked spectrum and its gradient stay
+    in registers.  Gradient flows to the raw mask only (spec = stft_custom(mixture) is data)."""
+
+    @staticmethod
+    def forward(ctx, spec, mask, length, n_fft, hop, win_length, scale, mode, pre_tanh):
+        nv.require_cuda_f32(spec, mask)
+        rows, nf, nt, _ = spec.shape
+        y = torch.empty((rows, length), dtype=torch.float32, device=spec.device)
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_mask_istft_fwd(spec.data_ptr(), mask.data_ptr(), y.data_ptr(), rows, nt, length, n_fft,
+                                                hop, win_length, scale, mode, int(pre_tanh), nv.stream_ptr(spec.device)))
+        ctx.save_for_backward(spec, mask)
+        ctx.cfg = (length, n_fft, hop, win_length, scale, mode, pre_tanh)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        spec, mask = ctx.saved_tensors
+        length, n_fft, hop, win_length, scale, mode, pre_tanh = ctx.cfg
+        rows, nf, nt, _ = spec.shape
+        gy = gy.contiguous()
+        gmask = torch.empty_like(mask)
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_mask_istft_bwd(gy.data_ptr(), spec.data_ptr(), mask.data_ptr(), gmask.data_ptr(), rows,
+                                                nt, length, n_fft, hop, win_length, scale, mode, int(pre_tanh),
+                                                nv.stream_ptr(spec.device)))
+        return None, gmask, None, None, None, None, None, None, None
+
+
+def mask_istft_rows(spec, mask, length, n_fft, hop, win_length, scale, mode, pre_tanh=False):
+    """spec [rows,F,T,2], mask [rows,F,T] ('real') or [rows,F,T,2] -> [rows,length]."""
+    _check_cfg(n_fft, hop, win_length)
+    if mode not in nv.MASK_MODES:
+        raise ValueError(f"unknown masking mode {mode!r}")
+    if spec.requires_grad:
+        # the spectrum itself is being trained through: keep the two differentiable stages separate
+        return istft(mask_apply(spec, mask, mode, pre_tanh), length, n_fft, hop, win_length, scale)
+    return _MaskISTFT.apply(_as_f32(spec).contiguous(), _as_f32(mask).contiguous(), int(length), n_fft, hop, win_length,
+                            float(scale), nv.MASK_MODES[mode], bool(pre_tanh))
+
+
 # ------------------------------------------------------------------ DCCRN conv transforms
 def conv_stft_rows(x, win_len, win_inc, fft_len):
     nv.require_cuda_f32(x)

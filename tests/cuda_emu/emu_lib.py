@@ -181,6 +181,22 @@ def enhance_bwd(gy, x, mask, n, hop, win, mode, pre_tanh):
     return out
 
 
+def mask_istft_fwd(spec, mask, length, n, hop, win, scale, mode, pre_tanh):
+    rows, F, T, _ = spec.shape
+    out = np.full((rows, length), np.nan, np.float32)
+    check(lib().se_mask_istft_fwd(ptr(spec), ptr(mask), ptr(out), i64(rows), i64(T), i64(length), ci(n), ci(hop), ci(win),
+                                  f32(scale), ci(mode), ci(int(pre_tanh)), None))
+    return out
+
+
+def mask_istft_bwd(gy, spec, mask, n, hop, win, scale, mode, pre_tanh):
+    rows, F, T, _ = spec.shape
+    out = np.full(mask.shape, np.nan, np.float32)
+    check(lib().se_mask_istft_bwd(ptr(gy), ptr(spec), ptr(mask), ptr(out), i64(rows), i64(T), i64(gy.shape[1]), ci(n),
+                                  ci(hop), ci(win), f32(scale), ci(mode), ci(int(pre_tanh)), None))
+    return out
+
+
 def stft_segments_fwd(x, nseg, seg_stride, nsample, n, hop, win, scale):
     nclip, clip_len = x.shape
     T = 1 + nsample // hop

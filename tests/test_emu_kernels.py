@@ -104,6 +104,39 @@ def test_emu_masks(mode, name, pre_tanh):
     assert rel(gs, np.nan_to_num(gs_.numpy())) < 1e-5
 
 
+@pytest.mark.parametrize("pre_tanh", [False, True])
+def test_emu_polar_mask_elementwise_accuracy_over_magnitude_ranges(pre_tanh):
+    """'E' mask per element (not max-norm): |m| from 1e-6 to 60 (series / rational / saturated tanh), |x| from 0
+    and 1e-20 (unit-vector path, like zero-filled segments) to 1e3."""
+    rng = np.random.default_rng(11)
+    mags_m = np.array([1e-6, 1e-3, 0.05, 0.0999, 0.1001, 0.3, 1.0, 3.0, 7.9, 8.0, 60.0])
+    mags_x = np.array([0.0, 1e-20, 1e-14, 1e-6, 1e-4, 1e-2, 1.0, 1e3])
+    ph = rng.uniform(0, 2 * np.pi, (2, mags_x.size, mags_m.size))
+    x = (mags_x[:, None] * np.exp(1j * ph[0]))
+    m = (mags_m[None, :] * np.exp(1j * ph[1]))
+    spec = np.ascontiguousarray(np.stack([x.real, x.imag], -1)[None].astype(np.float32))
+    mask = np.ascontiguousarray(np.stack([m.real, m.imag], -1)[None].astype(np.float32))
+    out = E.mask_fwd(spec, mask, 1, pre_tanh)
+    st = torch.from_numpy(spec).double()
+    mt = torch.from_numpy(mask).double().requires_grad_(True)
+    o = oref.mask_apply_ref(st, mt, "E", pre_tanh)
+    want = o.detach().numpy()
+    mag = np.sqrt((want ** 2).sum(-1, keepdims=True))
+    assert not np.isnan(out).any()
+    assert (np.abs(out - want) <= 3e-6 * mag + 1e-30).all()
+    go = rng.standard_normal(spec.shape).astype(np.float32)
+    (gm_,) = torch.autograd.grad(o, mt, torch.from_numpy(go).double())
+    gm, _ = E.mask_bwd(spec, mask, go, 1, pre_tanh)
+    gm_ = gm_.numpy()
+    gmag = np.sqrt((gm_ ** 2).sum(-1, keepdims=True))
+    live = np.broadcast_to(mags_x[None, :, None, None] > 0, gm.shape)      # atan2'(0,0) is undefined in the reference
+    assert not np.isnan(gm).any()
+    # past tanh's saturation the gradient is a difference of nearly equal terms: bound it against the scale of
+    # the terms (|x| |go|) as well
+    scale = np.sqrt((spec.astype(np.float64) ** 2).sum(-1, keepdims=True) + 1e-8) * np.sqrt((go.astype(np.float64) ** 2).sum(-1, keepdims=True))
+    assert (np.abs(gm - gm_)[live] <= (1e-5 * gmag + 1e-6 * scale + 1e-30)[np.broadcast_to(live[..., :1], gmag.shape)].repeat(2)).all()
+
+
 def test_emu_mask_matches_dcunet_and_dccrn_golden():
     g = golden("dcunet_mask_E")
     out = E.mask_fwd(np.ascontiguousarray(g["spec"]), np.ascontiguousarray(g["raw_mask"]), 1, True)
@@ -179,6 +212,33 @@ def test_emu_fused_enhance(n, hop, win, N, mode, name):
         (gm_ref,) = torch.autograd.grad(yr, mt, torch.from_numpy(gy)[:, None].double())
         gm = E.enhance_bwd(gy, x, m, n, hop, win, mode, pre_tanh)
         assert rel(gm, gm_ref.numpy()[:, 0]) < 2e-6
+
+
+@pytest.mark.parametrize("n,hop,win,N,length", [(512, 128, 512, 2085, 2085), (1024, 256, 1024, 4351, 4000),
+                                                (512, 256, 400, 3000, 3000), (2048, 512, 2048, 8705, 8705),
+                                                (1024, 512, 1024, 5000, 5200)])
+@pytest.mark.parametrize("mode,name", [(0, "real"), (1, "E"), (2, "C"), (3, "R")])
+def test_emu_mask_istft(n, hop, win, N, length, mode, name):
+    """Model tail + istft_custom in one launch, and its backward to the raw mask (spectrum never written)."""
+    rng = np.random.default_rng(7 * n + mode)
+    pre_tanh = mode in (1, 3)
+    F, T = n // 2 + 1, 1 + N // hop
+    if length > hop * (T - 1) + n // 2:
+        length = hop * (T - 1)
+    cfg = oref.make_config(n, hop, win)
+    spec = rng.standard_normal((2, F, T, 2)).astype(np.float32)
+    m = rng.standard_normal((2, F, T) if mode == 0 else (2, F, T, 2)).astype(np.float32)
+    y = E.mask_istft_fwd(spec, m, length, n, hop, win, float(win), mode, pre_tanh)
+    st = torch.from_numpy(spec)[:, None].double()
+    mt = torch.from_numpy(m)[:, None].double().requires_grad_(True)
+    yr = oref.istft_custom_ref(oref.mask_apply_ref(st, mt, name, pre_tanh), length, cfg)
+    assert not np.isnan(y).any()
+    assert rel(y, yr.detach().numpy()[:, 0]) < 2e-6
+    gy = rng.standard_normal((2, length)).astype(np.float32)
+    (gm_ref,) = torch.autograd.grad(yr, mt, torch.from_numpy(gy)[:, None].double())
+    gm = E.mask_istft_bwd(gy, spec, m, n, hop, win, float(win), mode, pre_tanh)
+    assert not np.isnan(gm).any()
+    assert rel(gm, gm_ref.numpy()[:, 0]) < 2e-6
 
 
 def test_emu_segment_stft_matches_reference_segmenting():

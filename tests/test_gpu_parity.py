@@ -325,6 +325,63 @@ def test_fused_enhance_matches_unfused_and_oracle(se, oref, n, h, w, N, mode):
     assert rel(gm2, gref) < TOL_GRAD
 
 
+@pytest.mark.parametrize("n,h,w,N,length", [(512, 128, 512, 16000, 16000), (512, 256, 512, 12345, 12345),
+                                            (1024, 256, 1024, 16384, 16000), (1024, 512, 1024, 30000, 30000),
+                                            (2048, 512, 2048, 44100, 44100), (2048, 1024, 2048, 40000, 39000),
+                                            (512, 128, 400, 9999, 9999)])
+@pytest.mark.parametrize("mode", ["real", "E", "C", "R"])
+def test_mask_istft_tail_matches_two_stage_and_oracle(se, oref, n, h, w, N, length, mode):
+    """apply_mask_istft == istft_custom(apply_mask(.)) (the masked spectrum is never written), fwd and bwd."""
+    g = torch.Generator().manual_seed(n + N + len(mode))
+    c = cfg(n, h, w)
+    pre_tanh = mode in ("E", "R")
+    F, T = n // 2 + 1, 1 + N // h
+    spec = torch.randn(2, 2, F, T, 2, generator=g)
+    mask = torch.randn(*((2, 2, F, T) if mode == "real" else (2, 2, F, T, 2)), generator=g)
+    mr = mask.double().requires_grad_(True)
+    ref = oref.istft_custom_ref(oref.mask_apply_ref(spec.double(), mr, mode, pre_tanh), length, c)
+    mc = mask.cuda().requires_grad_(True)
+    y = se.apply_mask_istft(spec.cuda(), mc, length, c, mode, pre_tanh)
+    assert y.shape == ref.shape
+    assert rel(y, ref) < TOL_SPEC
+    gy = torch.randn(ref.shape, generator=g)
+    (gref,) = torch.autograd.grad(ref, mr, gy.double())
+    (gm,) = torch.autograd.grad(y, mc, gy.cuda())
+    assert rel(gm, gref) < TOL_SPEC
+    m2 = mask.cuda().requires_grad_(True)
+    y2 = se.istft_custom(se.apply_mask(spec.cuda(), m2, mode, pre_tanh), length, c)
+    assert rel(y, y2) < 1e-5
+    (gm2,) = torch.autograd.grad(y2, m2, gy.cuda())
+    assert rel(gm, gm2) < 1e-5
+
+
+def test_mask_istft_tail_spectrum_requiring_grad_falls_back_to_two_stages(se):
+    c = cfg(512, 128, 512)
+    spec = torch.randn(1, 1, 257, 40, 2, device="cuda", requires_grad=True)
+    mask = torch.randn(1, 1, 257, 40, 2, device="cuda", requires_grad=True)
+    y = se.apply_mask_istft(spec, mask, 4992, c, "C")
+    gs, gm = torch.autograd.grad(y.square().sum(), (spec, mask))
+    s2, m2 = spec.detach().requires_grad_(True), mask.detach().requires_grad_(True)
+    y2 = se.istft_custom(se.apply_mask(s2, m2, "C"), 4992, c)
+    gs2, gm2 = torch.autograd.grad(y2.square().sum(), (s2, m2))
+    assert torch.equal(y, y2) and torch.equal(gs, gs2) and torch.equal(gm, gm2)
+
+
+def test_mask_istft_tail_full_size_cfg2(se):
+    """cfg2 at full size: the fused tail and the two-stage path agree, forward and backward."""
+    c = cfg(1024, 256, 1024)
+    spec = torch.randn(64, 1, 513, 251, 2, device="cuda")
+    raw = torch.randn(64, 1, 513, 251, 2, device="cuda")
+    gy = torch.randn(64, 1, 64000, device="cuda")
+    r1, r2 = raw.clone().requires_grad_(True), raw.clone().requires_grad_(True)
+    y1 = se.apply_mask_istft(spec, r1, 64000, c, "E", True)
+    y2 = se.istft_custom(se.apply_mask(spec, r2, "E", True), 64000, c)
+    assert float((y1 - y2).abs().max()) < 1e-5 * float(y2.abs().max())
+    (g1,) = torch.autograd.grad(y1, r1, gy)
+    (g2,) = torch.autograd.grad(y2, r2, gy)
+    assert float((g1 - g2).abs().max()) < 1e-5 * float(g2.abs().max())
+
+
 def test_fused_chain_full_size_cfg2(se):
     """cfg2 at full size: fused and unfused paths agree (size-independent consistency)."""
     c = cfg(1024, 256, 1024)
