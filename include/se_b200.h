@@ -168,6 +168,16 @@ int se_mask_istft_bwd(const float* gy, const float* spec, const float* mask, flo
                       int64_t nframe, int64_t length, int n_fft, int hop, int win_length, float scale, int mode,
                       int pre_tanh, void* stream);
 
+/* ---- Conv-TasNet decoder tail: overlap_and_add(signal, frame_step), src/model/conv_tasnet.py:11-31
+ * (called at :203 with frame_step = L/2).  signal [rows, frames, frame_length] ->
+ * out [rows, frame_step*(frames-1) + frame_length]; contributions are summed in increasing frame order
+ * (the order the reference's index_add_ applies them), deterministic, no atomics.
+ * bwd: gout [rows, out_len] -> gsignal [rows, frames, frame_length]. */
+int se_overlap_add_fwd(const float* signal, float* out, int64_t rows, int64_t frames, int frame_length,
+                       int frame_step, void* stream);
+int se_overlap_add_bwd(const float* gout, float* gsignal, int64_t rows, int64_t frames, int frame_length,
+                       int frame_step, void* stream);
+
 /* ---- DCCRN in-model transforms: ConvSTFT.forward / ConviSTFT.forward, src/model/dccrn.py:687-747
  * x [rows,N] -> spec [rows, 2F, T], T = (N + 2(win_len-win_inc) - win_len)/win_inc + 1, Hann
  * window, zero padding, frame zero-extended at the END to fft_len.  Supported: fft_len 512,

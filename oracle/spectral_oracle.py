@@ -316,3 +316,29 @@ def psa_loss_ref(enhance, target, mixture):
     amp_e = torch.sqrt(enhance[..., 1] ** 2 + enhance[..., 0] ** 2)
     amp_t = torch.sqrt(target[..., 1] ** 2 + target[..., 0] ** 2)
     return torch.mean((amp_e - amp_t * torch.cos(a_tgt - a_mix)) ** 2)
+
+
+def overlap_and_add_ref(signal, frame_step):
+    """src/model/conv_tasnet.py:11-31 restated without the sub-frame trick: frame f is added at offset
+    f*frame_step, frames in increasing order (the order the reference's index_add_ applies its rows)."""
+    outer = tuple(signal.shape[:-2])
+    frames, length = signal.shape[-2:]
+    out = signal.new_zeros(*outer, frame_step * (frames - 1) + length)
+    for f in range(frames):
+        out[..., f * frame_step:f * frame_step + length] += signal[..., f, :]
+    return out
+
+
+def si_sdr_metric_ref(reference, estimation):
+    """SI_SDR of src/metric.py:92-123 (numpy there; mean of the per-row energy ratios, then dB; eps = the
+    input dtype's machine epsilon)."""
+    import numpy as np
+    r = reference.detach().cpu().numpy() if torch.is_tensor(reference) else np.asarray(reference)
+    e = estimation.detach().cpu().numpy() if torch.is_tensor(estimation) else np.asarray(estimation)
+    energy = np.sum(r ** 2, axis=-1, keepdims=True)
+    eps = np.finfo(energy.dtype).eps
+    scale = np.sum(e * r, axis=-1, keepdims=True) / (energy + eps)
+    proj = scale * r
+    noise = e - proj
+    ratio = np.mean(np.sum(proj ** 2, axis=-1) / (np.sum(noise ** 2, axis=-1) + eps))
+    return 10 * np.log10(ratio + eps)

@@ -13,15 +13,18 @@ Public surface (all CUDA-only, no CPU fallback):
     ConvSTFT, ConviSTFT                src/model/dccrn.py:669-747
     enhance                            fused stft_custom -> mask -> istft_custom
     apply_mask_istft                   fused model tail -> istft_custom (masked spectrum never written)
+    si_snr, loss_sisdr, SI_SDR         src/loss.py:14-29, src/metric.py:92-123
+    overlap_and_add                    src/model/conv_tasnet.py:11-31
 """
 from .evaluate import stft_custom, istft_custom, stft_custom_with_feature, evaluate, segment_stft, stitch_segments
 from .masking import apply_mask, apply_mask_dccrn, magnitude_feature
 from .loss import (loss_mrstft, MRSTFTLoss, loss_spectral, si_snr, loss_sisdr,
-                   loss_phase_sensitive_spectral_approximation)
+                   loss_phase_sensitive_spectral_approximation, SI_SDR)
+from .tasnet import overlap_and_add
 from .dccrn import ConvSTFT, ConviSTFT
 from .fused import enhance, apply_mask_istft
 from . import _native
 
 __all__ = ["stft_custom", "istft_custom", "stft_custom_with_feature", "magnitude_feature", "evaluate", "segment_stft", "stitch_segments", "apply_mask", "apply_mask_dccrn", "loss_mrstft", "MRSTFTLoss", "loss_spectral", "si_snr", "loss_sisdr", "loss_phase_sensitive_spectral_approximation",
-           "ConvSTFT", "ConviSTFT", "enhance", "apply_mask_istft"]
+           "ConvSTFT", "ConviSTFT", "enhance", "apply_mask_istft", "SI_SDR", "overlap_and_add"]
 __version__ = "0.1.0"

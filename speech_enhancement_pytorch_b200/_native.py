@@ -24,7 +24,7 @@ EXPORTS = (
     "se_mask_fwd", "se_mask_bwd", "se_mrstft_workspace_bytes", "se_mrstft_loss_fwd",
     "se_mrstft_loss_value", "se_mrstft_loss_bwd", "se_spectral_loss_workspace_bytes", "se_spectral_loss_fwd",
     "se_spectral_loss_bwd", "se_sisnr_fwd", "se_sisnr_bwd", "se_psa_workspace_bytes", "se_psa_loss_fwd", "se_psa_loss_bwd", "se_enhance_fwd", "se_enhance_bwd",
-    "se_mask_istft_fwd", "se_mask_istft_bwd",
+    "se_mask_istft_fwd", "se_mask_istft_bwd", "se_overlap_add_fwd", "se_overlap_add_bwd",
     "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
 )
 
@@ -129,6 +129,8 @@ def lib():
             L.se_enhance_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
             L.se_mask_istft_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _INT, _PTR]
             L.se_mask_istft_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _INT, _PTR]
+            L.se_overlap_add_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _PTR]
+            L.se_overlap_add_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _PTR]
             L.se_conv_stft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _PTR]
             L.se_conv_istft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]
             L.se_conv_istft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]

@@ -72,3 +72,23 @@ def loss_phase_sensitive_spectral_approximation(enhance, target, mixture, group=
     `psa` loss, src/distrib.py:271-272; called with the mixture as third argument, src/solver.py:477-480),
     one fused elementwise-and-reduce pass over the three spectra [...,F,T,2]."""
     return ops.psa_loss(enhance, target, mixture, group)
+
+
+def SI_SDR(reference, estimation, sr=16000):
+    """`SI_SDR(reference, estimation)` of src/metric.py:92-123 on device tensors [...,T]: the three inner products
+    per row come from one pass over both waveforms (the SI-SNR kernel), the per-row ratio, its mean and the
+    10 log10 follow the reference's order (mean of the energy RATIOS, then dB; eps = float32 machine epsilon).
+    Returns a 0-dim float64 tensor on the device (no host sync); no gradient (a metric)."""
+    import torch
+    if reference.shape != estimation.shape:
+        raise ValueError(f"shape mismatch {tuple(reference.shape)} vs {tuple(estimation.shape)}")
+    n = reference.shape[-1]
+    with torch.no_grad():
+        d = ops.row_dots(estimation.reshape(-1, n), reference.reshape(-1, n))      # <e,e>, <e,r>, <r,r>
+        eps = float(torch.finfo(torch.float32).eps)
+        ee, er, rr = d[:, 0], d[:, 1], d[:, 2]
+        alpha = er / (rr + eps)
+        proj = alpha * alpha * rr
+        noise = (ee - 2.0 * alpha * er + proj).clamp_min(0.0)
+        ratio = (proj / (noise + eps)).mean()
+        return 10.0 * torch.log10(ratio + eps)

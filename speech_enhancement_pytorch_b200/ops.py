@@ -395,6 +395,49 @@ def mask_istft_rows(spec, mask, length, n_fft, hop, win_length, scale, mode, pre
                             float(scale), nv.MASK_MODES[mode], bool(pre_tanh))
 
 
+class _OverlapAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, signal, frame_step):
+        nv.require_cuda_f32(signal)
+        rows, frames, length = signal.shape
+        out = torch.empty((rows, frame_step * (frames - 1) + length), dtype=torch.float32, device=signal.device)
+        with nv.on_device(signal.device):
+            nv.check(nv.lib().se_overlap_add_fwd(signal.data_ptr(), out.data_ptr(), rows, frames, length, frame_step,
+                                                 nv.stream_ptr(signal.device)))
+        ctx.cfg = (rows, frames, length, frame_step)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        rows, frames, length, frame_step = ctx.cfg
+        gout = gout.contiguous()
+        g = torch.empty((rows, frames, length), dtype=torch.float32, device=gout.device)
+        with nv.on_device(gout.device):
+            nv.check(nv.lib().se_overlap_add_bwd(gout.data_ptr(), g.data_ptr(), rows, frames, length, frame_step,
+                                                 nv.stream_ptr(gout.device)))
+        return g, None
+
+
+def overlap_add_rows(signal_rows, frame_step):
+    """signal [rows, frames, frame_length] -> [rows, frame_step*(frames-1) + frame_length]."""
+    if int(frame_step) <= 0:
+        raise ValueError("frame_step must be positive")
+    return _OverlapAdd.apply(_as_f32(signal_rows).contiguous(), int(frame_step))
+
+
+def row_dots(s1_rows, s2_rows):
+    """<s1,s1>, <s1,s2>, <s2,s2> per row in float64 ([rows,3]) -- one pass over both waveforms (se_sisnr_fwd)."""
+    s1, s2 = _as_f32(s1_rows).contiguous(), _as_f32(s2_rows).contiguous()
+    nv.require_cuda_f32(s1, s2)
+    rows, n = s1.shape
+    dots = torch.empty(rows, 3, dtype=torch.float64, device=s1.device)
+    snr = torch.empty(rows, dtype=torch.float32, device=s1.device)
+    with nv.on_device(s1.device):
+        nv.check(nv.lib().se_sisnr_fwd(s1.data_ptr(), s2.data_ptr(), rows, n, 1e-8, dots.data_ptr(), snr.data_ptr(),
+                                       nv.stream_ptr(s1.device)))
+    return dots
+
+
 # ------------------------------------------------------------------ DCCRN conv transforms
 def conv_stft_rows(x, win_len, win_inc, fft_len):
     nv.require_cuda_f32(x)

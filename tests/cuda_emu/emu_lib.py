@@ -197,6 +197,20 @@ def mask_istft_bwd(gy, spec, mask, n, hop, win, scale, mode, pre_tanh):
     return out
 
 
+def overlap_add_fwd(sig, step):
+    rows, frames, length = sig.shape
+    out = np.full((rows, step * (frames - 1) + length), np.nan, np.float32)
+    check(lib().se_overlap_add_fwd(ptr(sig), ptr(out), i64(rows), i64(frames), ci(length), ci(step), None))
+    return out
+
+
+def overlap_add_bwd(gout, frames, length, step):
+    rows = gout.shape[0]
+    out = np.full((rows, frames, length), np.nan, np.float32)
+    check(lib().se_overlap_add_bwd(ptr(gout), ptr(out), i64(rows), i64(frames), ci(length), ci(step), None))
+    return out
+
+
 def stft_segments_fwd(x, nseg, seg_stride, nsample, n, hop, win, scale):
     nclip, clip_len = x.shape
     T = 1 + nsample // hop

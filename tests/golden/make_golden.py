@@ -168,7 +168,41 @@ def gen_segments():
     save("segments", wav=wav, seg=seg, meta=np.array([2048, 512]))
 
 
+def gen_tasnet_and_metric():
+    """Conv-TasNet's overlap_and_add (src/model/conv_tasnet.py:11-31) and the SI_SDR metric (src/metric.py:92-123).
+    src.metric imports pesq / pypesq / pystoi / museval at module level (absent here, unused by SI_SDR): they
+    are stubbed for the import only."""
+    import types
+    from src.model.conv_tasnet import overlap_and_add
+    for name in ("pesq", "pypesq", "pystoi", "museval", "museval.metrics"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["pesq"].pesq = sys.modules["pesq"].cypesq = None
+    sys.modules["pypesq"].pesq = None
+    sys.modules["pystoi"].stoi = None
+    sys.modules["museval.metrics"].bss_eval = None
+    sys.modules["museval"].metrics = sys.modules["museval.metrics"]
+    from src.metric import SI_SDR
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for tag, (shape, step) in {"half": ((2, 3, 50, 40), 20), "quarter": ((3, 37, 32), 8), "coprime": ((2, 9, 10), 4),
+                               "gap": ((2, 6, 8), 12), "abut": ((1, 5, 16), 16)}.items():
+        sig = torch.randn(*shape, generator=g)
+        out[f"sig_{tag}"] = sig
+        out[f"step_{tag}"] = np.array(step)
+        out[f"out_{tag}"] = overlap_and_add(sig, step)
+    ref = torch.randn(3, 2, 4000, generator=g)
+    est = ref + 0.3 * torch.randn(3, 2, 4000, generator=g)
+    out["sdr_ref"], out["sdr_est"] = ref, est
+    out["sdr"] = np.array(SI_SDR(ref, est), dtype=np.float64)
+    out["sdr_scaled"] = np.array(SI_SDR(ref, 0.01 * est + 0.5), dtype=np.float64)
+    save("tasnet_metric", **out)
+
+
 if __name__ == "__main__":
+    gen_tasnet_and_metric()
+    if "--only-new" in sys.argv:
+        sys.exit(0)
     gen_stft_istft()
     gen_grads()
     gen_conv()

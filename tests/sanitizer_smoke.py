@@ -26,6 +26,9 @@ def main():
         y.sum().backward()
         y2 = se.enhance(x.detach(), m, c, "C")
         y2.square().mean().backward()
+        for mode in ("real", "E", "C", "R"):
+            mm = torch.randn(*(spec.shape[:-1] if mode == "real" else spec.shape), device=dev, requires_grad=True)
+            se.apply_mask_istft(spec.detach(), mm, N, c, mode, mode == "E").square().sum().backward()
         sp, ft = se.stft_custom_with_feature(x.detach(), c, "amplitude")
         tgt = torch.randn(2, 1, N, device=dev)
         e = spec.detach().clone().requires_grad_(True)
@@ -34,6 +37,10 @@ def main():
     ref = torch.randn(3, 1, 7000, device=dev)
     se.loss_mrstft(est, ref).backward()
     se.loss_sisdr(est, ref).backward()
+    se.SI_SDR(ref, est.detach())
+    frames = torch.randn(2, 3, 57, 40, device=dev, requires_grad=True)
+    se.overlap_and_add(frames, 20).sum().backward()
+    se.overlap_and_add(torch.randn(3, 9, 10, device=dev), 4)
     st, ist = se.ConvSTFT(400, 100, 512, "hann", "complex"), se.ConviSTFT(400, 100, 512, 3000, "hann", "complex")
     s = st(torch.randn(2, 1, 3000, device=dev)).requires_grad_(True)
     ist(s).sum().backward()

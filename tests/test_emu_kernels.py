@@ -326,3 +326,20 @@ def test_emu_edge_lengths(n, hop):
             gx = E.stft_bwd(r2(spec), N, n, hop, n, 1.0 / n)
             assert not np.isnan(gx).any(), N
             assert rel(gx, o64.stft_adjoint(c2(r2(spec)), N, n, hop, n)) < 5e-6, N
+
+
+@pytest.mark.parametrize("tag", ["half", "quarter", "coprime", "gap", "abut"])
+def test_emu_overlap_and_add_matches_reference_golden_and_autograd(tag):
+    """Conv-TasNet decoder tail (src/model/conv_tasnet.py:11-31): bit-exact (same summation order); the backward
+    is the exact gather."""
+    g = golden("tasnet_metric")
+    sig, step = g[f"sig_{tag}"], int(g[f"step_{tag}"])
+    frames, length = sig.shape[-2:]
+    rows = np.ascontiguousarray(sig.reshape(-1, frames, length))
+    out = E.overlap_add_fwd(rows, step)
+    assert np.array_equal(out.reshape(g[f"out_{tag}"].shape), g[f"out_{tag}"])
+    rng = np.random.default_rng(3)
+    go = rng.standard_normal(out.shape).astype(np.float32)
+    st = torch.from_numpy(rows).requires_grad_(True)
+    (gw,) = torch.autograd.grad(oref.overlap_and_add_ref(st, step), st, torch.from_numpy(go))
+    assert np.array_equal(E.overlap_add_bwd(go, frames, length, step), gw.numpy())

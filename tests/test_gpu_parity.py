@@ -546,6 +546,43 @@ def test_si_snr_and_gradient(se, oref, shape, noise):
     assert abs(float(got) + float(oref.si_snr_ref(est, tgt))) < 1e-3 * max(1.0, abs(float(want)))
 
 
+@pytest.mark.parametrize("tag", ["half", "quarter", "coprime", "gap", "abut"])
+def test_overlap_and_add_matches_reference_golden(se, oref, tag):
+    """8f-4: Conv-TasNet's overlap_and_add (src/model/conv_tasnet.py:11-31): bit-exact, gradient = exact gather."""
+    g = golden("tasnet_metric")
+    sig, step = torch.from_numpy(g[f"sig_{tag}"]), int(g[f"step_{tag}"])
+    sc = sig.cuda().requires_grad_(True)
+    out = se.overlap_and_add(sc, step)
+    assert out.shape == g[f"out_{tag}"].shape
+    assert np.array_equal(out.detach().cpu().numpy(), g[f"out_{tag}"])
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(1))
+    sr = sig.clone().requires_grad_(True)
+    (gw,) = torch.autograd.grad(oref.overlap_and_add_ref(sr, step), sr, go)
+    (gg,) = torch.autograd.grad(out, sc, go.cuda())
+    assert torch.equal(gg.cpu(), gw)
+
+
+def test_overlap_and_add_conv_tasnet_size(se, oref):
+    """Decoder output of Conv-TasNet for a 4 s batch: [M, C, K, L] = [8, 2, 3199, 40], step L/2 (conv_tasnet.py:203)."""
+    sig = torch.randn(8, 2, 3199, 40, generator=torch.Generator().manual_seed(5))
+    out = se.overlap_and_add(sig.cuda(), 20)
+    assert out.shape == (8, 2, 64000)
+    assert torch.equal(out.cpu(), oref.overlap_and_add_ref(sig, 20))
+
+
+def test_si_sdr_metric_matches_reference_golden(se, oref):
+    """8f-4: SI_SDR (src/metric.py:92-123) from one pass over the two waveforms."""
+    g = golden("tasnet_metric")
+    ref, est = torch.from_numpy(g["sdr_ref"]).cuda(), torch.from_numpy(g["sdr_est"]).cuda()
+    got = se.SI_SDR(ref, est)
+    assert got.dim() == 0 and got.is_cuda
+    assert abs(float(got) - float(g["sdr"])) < 1e-4
+    assert abs(float(se.SI_SDR(ref, 0.01 * est + 0.5)) - float(g["sdr_scaled"])) < 1e-4
+    big_r = torch.randn(4, 1, 64000, generator=torch.Generator().manual_seed(2))
+    big_e = big_r * 0.5 + 0.2 * torch.randn(4, 1, 64000, generator=torch.Generator().manual_seed(3))
+    assert abs(float(se.SI_SDR(big_r.cuda(), big_e.cuda())) - float(oref.si_sdr_metric_ref(big_r.double(), big_e.double()))) < 1e-4
+
+
 def test_reentrant_from_threads_on_separate_streams(se, oref):
     """nn.DataParallel runs DCCRN's transforms from one Python thread per GPU (src/solver.py:145): the C-ABI
     must be re-entrant.  Two threads, two streams, different configurations, results checked per thread."""

@@ -129,3 +129,20 @@ def test_mrstft_loss_fp32_vs_f64_and_gradient():
     l64, g64 = o64.mrstft_loss(est.detach().numpy(), ref.numpy(), with_grad=True)
     assert abs(float(loss.detach()) - l64) / l64 < 1e-5
     assert rel(grad.numpy().reshape(2, -1), g64) < 1e-3   # fp32 torch itself sits ~5e-4 from f64 here
+
+
+OLA_TAGS = ("half", "quarter", "coprime", "gap", "abut")
+
+
+@pytest.mark.parametrize("tag", OLA_TAGS)
+def test_overlap_and_add_oracle_matches_reference(tag):
+    g = golden("tasnet_metric")
+    out = oref.overlap_and_add_ref(torch.from_numpy(g[f"sig_{tag}"]), int(g[f"step_{tag}"]))
+    assert out.shape == g[f"out_{tag}"].shape
+    assert np.array_equal(out.numpy(), g[f"out_{tag}"])      # same summation order -> bit exact
+
+
+def test_si_sdr_metric_oracle_matches_reference():
+    g = golden("tasnet_metric")
+    assert abs(oref.si_sdr_metric_ref(g["sdr_ref"], g["sdr_est"]) - float(g["sdr"])) < 1e-6
+    assert abs(oref.si_sdr_metric_ref(g["sdr_ref"], 0.01 * g["sdr_est"] + 0.5) - float(g["sdr_scaled"])) < 1e-5
