@@ -61,8 +61,9 @@ def cpu_chain(rows, nsample, steps, warmup, threads=None):
     import types
     import torch
     from oracle import spectral_oracle as oref
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    threads = threads or len(os.sched_getaffinity(0)) or os.cpu_count() or 1
+    torch.set_num_threads(threads)
     cfg = types.SimpleNamespace(n_fft=N_FFT, hop_length=HOP, win_length=WIN, center=True)
     g = torch.Generator().manual_seed(1235)
     x = torch.randn(rows, 1, nsample, generator=g)
