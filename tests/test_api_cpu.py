@@ -48,3 +48,29 @@ def test_modules_keep_reference_attributes():
     assert (st.fft_len, st.stride, st.win_len, st.dim) == (512, 100, 400, 512)
     ist = se.ConviSTFT(400, 100, 512, 16384, "hann", "complex")
     assert (ist.length, ist.stride, ist.win_len) == (16384, 100, 400)
+
+
+def test_fused_tail_and_tasnet_entry_points_validate_without_a_gpu():
+    spec, mask = torch.randn(1, 1, 257, 33, 2), torch.randn(1, 1, 257, 33, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.apply_mask_istft(spec, mask, 4096, cfg(), "E", True)
+    with pytest.raises(ValueError):
+        se.apply_mask_istft(spec, mask[..., 0], 4096, cfg(), "E")            # complex modes need [...,F,T,2]
+    with pytest.raises(ValueError):
+        se.apply_mask_istft(spec, mask, 4096, cfg(), "Z")
+    with pytest.raises(ValueError):
+        se.apply_mask_istft(spec[0, 0], mask[0, 0], 4096, cfg(), "C")        # 5-D / 6-D only, like istft_custom
+    with pytest.raises(RuntimeError):
+        se.apply_mask_istft(torch.randn(1, 1, 129, 33, 2), torch.randn(1, 1, 129, 33, 2), 4096, cfg(), "C")
+    with pytest.raises(NotImplementedError):
+        se.apply_mask_istft(spec, mask, 4096, cfg(512, 100, 512), "C")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.overlap_and_add(torch.randn(2, 5, 40), 20)
+    with pytest.raises(ValueError):
+        se.overlap_and_add(torch.randn(40), 20)
+    with pytest.raises(ValueError):
+        se.overlap_and_add(torch.randn(2, 5, 40), 0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.SI_SDR(torch.randn(2, 100), torch.randn(2, 100))
+    with pytest.raises(ValueError):
+        se.SI_SDR(torch.randn(2, 100), torch.randn(2, 99))
