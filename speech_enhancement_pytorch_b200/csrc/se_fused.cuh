@@ -28,6 +28,20 @@ __device__ __forceinline__ float2 load_mask(const EnhArgs& a, size_t row, int k,
     return __ldg(reinterpret_cast<const float2*>(a.mask) + idx);
 }
 
+// Raw-mask value of one bin through a pointer that walks a unit's 8 bins (S*T apart): real masks are float
+// rows, the complex modes float2 rows (see store_task_ft2 for why pointers are walked instead of re-indexed).
+template <int MODE>
+struct MaskWalk {
+    const float* p;
+    size_t step;
+    __device__ __forceinline__ MaskWalk(const float* mask, size_t idx, size_t step_) : p(mask + (MODE == 0 ? idx : 2 * idx)), step(MODE == 0 ? step_ : 2 * step_) {}
+    __device__ __forceinline__ float2 next() {
+        const float2 v = MODE == 0 ? make_float2(__ldg(p), 0.f) : __ldg(reinterpret_cast<const float2*>(p));
+        p += step;
+        return v;
+    }
+};
+
 template <class G, int MODE, bool TANH>
 __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a) {
     SE_SMEM_DECL;
@@ -64,10 +78,14 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_enhance_fwd(const EnhArgs a)
             const int qa = task_qa<G>(p), qb = task_qb<G>(p);
             // mask values first: 17 independent loads in flight while pass C runs
             float2 ma[8], mb[8], mn;
+            {
+                const size_t rb = (size_t)row * G::F * a.nframe + tc, step = (size_t)G::S * a.nframe;
+                MaskWalk<MODE> wa(a.mask, rb + (size_t)qa * a.nframe, step), wb(a.mask, rb + (size_t)qb * a.nframe, step);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                ma[k] = load_mask<G, MODE>(a, row, qa + G::S * k, tc);
-                mb[k] = load_mask<G, MODE>(a, row, qb + G::S * k, tc);
+                for (int k = 0; k < 8; ++k) {
+                    ma[k] = wa.next();
+                    mb[k] = wb.next();
+                }
             }
             mn = load_mask<G, MODE>(a, row, G::M, tc);
             float2 xa[8], xb[8], nyq;
@@ -128,22 +146,25 @@ __global__ void __launch_bounds__(G::NT) k_enhance_bwd(const EnhArgs a) {
             for (int half = 0; half < 2; ++half) {               // unit a, then unit b: 8 bins each (+ Nyquist)
                 const int q = half ? qb : qa;
                 float2 m[8], mn = make_float2(0.f, 0.f);
+                {
+                    MaskWalk<MODE> w(a.mask, (size_t)row * G::F * a.nframe + (size_t)q * a.nframe + tc, (size_t)G::S * a.nframe);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) m[k] = load_mask<G, MODE>(a, row, q + G::S * k, tc);
+                    for (int k = 0; k < 8; ++k) m[k] = w.next();
+                }
                 if (half == 0) mn = load_mask<G, MODE>(a, row, G::M, tc);
                 float2 xa[8], xb[8], xn, ga[8], gb[8], gn;
                 analysis_task<G>(zbx, ta, p, fr, xa, xb, xn);
                 analysis_task<G>(zbg, ts, p, fr, ga, gb, gn);
                 if (!live) continue;
+                const size_t obase = (size_t)row * G::F * a.nframe + (size_t)q * a.nframe + t, ostep = (size_t)G::S * a.nframe;
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     if (k == 8 && (half != 0 || p != 0)) continue;
-                    const int bin = k < 8 ? q + G::S * k : G::M;
                     const float2 x = k < 8 ? (half ? xb[k] : xa[k]) : xn;
                     float2 gy = k < 8 ? (half ? gb[k] : ga[k]) : gn;
                     // iSTFT adjoint: c_k / n with the 2/n folded into the window -> edges get 1/2, real only
                     if (p == 0 && half == 0 && (k == 0 || k == 8)) gy = make_float2(0.5f * gy.x, 0.f);
-                    const size_t idx = ((size_t)row * G::F + bin) * (size_t)a.nframe + t;
+                    const size_t idx = k < 8 ? obase + (size_t)k * ostep : (size_t)row * G::F * a.nframe + (size_t)G::M * a.nframe + t;
                     float2 gm, gx;
                     MaskMath::grad<MODE, TANH>(x, k < 8 ? m[k] : mn, gy, gm, gx);
                     if (MODE == 0) a.out[idx] = gm.x;
@@ -213,12 +234,19 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_mask_istft_fwd(const MaskSyn
             const int p = unit + i * G::NU;
             const int qa = task_qa<G>(p), qb = task_qb<G>(p);
             float2 ya[8], yb[8], nyq;
+            {
+                const size_t step = (size_t)G::S * a.nframe, ia = (size_t)qa * a.nframe + tc, ib = (size_t)qb * a.nframe + tc;
+                const float2* sa = spec + ia;
+                const float2* sb = spec + ib;
+                MaskWalk<MODE> wa(a.mask, rbase + ia, step), wb(a.mask, rbase + ib, step);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const size_t ia = (size_t)(qa + G::S * k) * a.nframe + tc, ib = (size_t)(qb + G::S * k) * a.nframe + tc;
-                ya[k] = MaskMath::apply<MODE, TANH>(__ldg(spec + ia), load_mask_at<G, MODE>(a.mask, rbase + ia));
-                yb[k] = MaskMath::apply<MODE, TANH>(__ldg(spec + ib), load_mask_at<G, MODE>(a.mask, rbase + ib));
-                if (!live) ya[k] = yb[k] = make_float2(0.f, 0.f);
+                for (int k = 0; k < 8; ++k) {
+                    ya[k] = MaskMath::apply<MODE, TANH>(__ldg(sa), wa.next());
+                    yb[k] = MaskMath::apply<MODE, TANH>(__ldg(sb), wb.next());
+                    if (!live) ya[k] = yb[k] = make_float2(0.f, 0.f);
+                    sa += step;
+                    sb += step;
+                }
             }
             nyq = make_float2(0.f, 0.f);
             if (p == 0 && live) {
@@ -235,6 +263,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_mask_istft_fwd(const MaskSyn
 template <class G, int MODE, bool TANH>
 __device__ __forceinline__ void mask_grad_half(const MaskSynArgs& a, const float2* x, const float2* m, const float2* gy,
                                                size_t rbase, int q, int t, bool edge) {
+    size_t idx = rbase + (size_t)q * a.nframe + t;
+    const size_t step = (size_t)G::S * a.nframe;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         float2 g = gy[k];
@@ -242,9 +272,9 @@ __device__ __forceinline__ void mask_grad_half(const MaskSynArgs& a, const float
         if (k == 0 && edge) g = make_float2(0.5f * g.x, 0.f);
         float2 gm, gx;
         MaskMath::grad<MODE, TANH>(x[k], m[k], g, gm, gx);
-        const size_t idx = rbase + (size_t)(q + G::S * k) * a.nframe + t;
         if (MODE == 0) a.out[idx] = gm.x;
         else reinterpret_cast<float2*>(a.out)[idx] = gm;
+        idx += step;
     }
 }
 
@@ -276,20 +306,31 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_mask_istft_bwd(const MaskSyn
             const int p = unit + i * G::NU;
             const int qa = task_qa<G>(p), qb = task_qb<G>(p);
             float2 x[8], m[8];
+            const size_t step = (size_t)G::S * a.nframe;
+            {                                              // unit a's operands in flight while pass C runs
+                const size_t ia = (size_t)qa * a.nframe + tc;
+                const float2* sa = spec + ia;
+                MaskWalk<MODE> wa(a.mask, rbase + ia, step);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {                  // unit a's operands in flight while pass C runs
-                const size_t idx = (size_t)(qa + G::S * k) * a.nframe + tc;
-                x[k] = __ldg(spec + idx);
-                m[k] = load_mask_at<G, MODE>(a.mask, rbase + idx);
+                for (int k = 0; k < 8; ++k) {
+                    x[k] = __ldg(sa);
+                    m[k] = wa.next();
+                    sa += step;
+                }
             }
             float2 ga[8], gb[8], gn;
             analysis_task<G>(zb, tb, p, fr, ga, gb, gn);
             if (live) mask_grad_half<G, MODE, TANH>(a, x, m, ga, rbase, qa, t, p == 0);
+            {
+                const size_t ib = (size_t)qb * a.nframe + tc;
+                const float2* sb = spec + ib;
+                MaskWalk<MODE> wb(a.mask, rbase + ib, step);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const size_t idx = (size_t)(qb + G::S * k) * a.nframe + tc;
-                x[k] = __ldg(spec + idx);
-                m[k] = load_mask_at<G, MODE>(a.mask, rbase + idx);
+                for (int k = 0; k < 8; ++k) {
+                    x[k] = __ldg(sb);
+                    m[k] = wb.next();
+                    sb += step;
+                }
             }
             if (live) mask_grad_half<G, MODE, TANH>(a, x, m, gb, rbase, qb, t, false);
             if (p == 0 && live) {                          // Nyquist

@@ -174,21 +174,38 @@ static __global__ void __launch_bounds__(256) k_feature(const float2* __restrict
 
 // ------------------------------------------------------------------ spectrum row I/O
 // interleaved [F][T] float2
+// Addressing: the 8 bins of a unit are S*T float2 apart, so each unit walks ONE 64-bit pointer by a constant
+// stride (two integer instructions per access).  Indexing every access as row[(q + S k) T + t] made the compiler
+// rebuild the full 64-bit address each time -- 17 integer instructions per pair of stores in the ncu source view.
 template <class G>
 __device__ __forceinline__ void store_task_ft2(float2* __restrict__ row, int T, int t, int p,
                                                const float2* xa, const float2* xb, float2 nyq, float edge,
                                                float* __restrict__ frow = nullptr, int kind = 0) {
     if (t < 0 || t >= T) return;
-    const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+    const size_t step = (size_t)G::S * T;
+    const size_t ia = (size_t)task_qa<G>(p) * T + t, ib = (size_t)task_qb<G>(p) * T + t;
+    float2* pa = row + ia;
+    float2* pb = row + ib;
+    const float2 dc = make_float2(xa[0].x * edge, 0.f);
+    if (frow == nullptr) {
 #pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-        float2 v = xa[k4];
-        if (p == 0 && k4 == 0) v = make_float2(v.x * edge, 0.f);
-        row[(size_t)(qa + G::S * k4) * T + t] = v;
-        row[(size_t)(qb + G::S * k4) * T + t] = xb[k4];
-        if (frow) {                                   // the NN's input feature, written while the bin is in registers
-            frow[(size_t)(qa + G::S * k4) * T + t] = feature_of(v, kind);
-            frow[(size_t)(qb + G::S * k4) * T + t] = feature_of(xb[k4], kind);
+        for (int k4 = 0; k4 < 8; ++k4) {
+            *pa = (p == 0 && k4 == 0) ? dc : xa[k4];
+            *pb = xb[k4];
+            pa += step;
+            pb += step;
+        }
+    } else {                                          // the NN's input feature, written while the bin is in registers
+        float* fa = frow + ia;
+        float* fb = frow + ib;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+            const float2 v = (p == 0 && k4 == 0) ? dc : xa[k4];
+            *pa = v;
+            *pb = xb[k4];
+            *fa = feature_of(v, kind);
+            *fb = feature_of(xb[k4], kind);
+            pa += step; pb += step; fa += step; fb += step;
         }
     }
     if (p == 0) {
@@ -220,15 +237,25 @@ template <class G>
 __device__ __forceinline__ void load_task_ft2(const float2* __restrict__ row, int T, int t, int p,
                                               float2* ya, float2* yb, float2& nyq, float edge) {
     const bool ok = (t >= 0 && t < T);
-    const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+    const int tc = ok ? t : 0;                                   // clamped: loads stay in bounds, result zeroed
+    const size_t step = (size_t)G::S * T;
+    const float2* pa = row + (size_t)task_qa<G>(p) * T + tc;
+    const float2* pb = row + (size_t)task_qb<G>(p) * T + tc;
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
-        ya[k4] = ok ? __ldg(row + (size_t)(qa + G::S * k4) * T + t) : make_float2(0.f, 0.f);
-        yb[k4] = ok ? __ldg(row + (size_t)(qb + G::S * k4) * T + t) : make_float2(0.f, 0.f);
+        ya[k4] = __ldg(pa);
+        yb[k4] = __ldg(pb);
+        pa += step;
+        pb += step;
     }
     nyq = make_float2(0.f, 0.f);
+    if (p == 0) nyq = __ldg(row + (size_t)G::M * T + tc);
+    if (!ok) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) ya[k4] = yb[k4] = make_float2(0.f, 0.f);
+        nyq = make_float2(0.f, 0.f);
+    }
     if (p == 0) {
-        if (ok) nyq = __ldg(row + (size_t)G::M * T + t);
         ya[0].x *= edge;
         nyq.x *= edge;
     }
@@ -575,17 +602,23 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
                 const int p = unit + i * G::NU;
                 float2 xa[8], xb[8], nyq;
                 analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
+                // |B| rows of this task: one pointer per unit walked by S*T (see store_task_ft2)
+                float* mrow = a.refmag + (size_t)row * G::F * a.nframe + t;
+                const size_t mstep = (size_t)G::S * a.nframe;
+                float* wp = mrow + (size_t)task_qa<G>(p) * a.nframe;
 #pragma unroll
                 for (int k = 0; k < 17; ++k) {
                     const float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
                     const float pw = v.x * v.x + v.y * v.y;
                     if (sig == 0) {
                         pb[i][k] = pw;
+                        if (k == 8) wp = mrow + (size_t)task_qb<G>(p) * a.nframe;
+                        if (k == 16) wp = mrow + (size_t)G::M * a.nframe;
                         if (t < a.nframe && !(k == 16 && p != 0)) {      // keep |B| for the backward pass
                             const float cb = fmaxf(pw, SE_MRSTFT_CLAMP);
-                            const int bin = k < 8 ? task_qa<G>(p) + G::S * k : (k < 16 ? task_qb<G>(p) + G::S * (k - 8) : G::M);
-                            a.refmag[((size_t)row * G::F + bin) * (size_t)a.nframe + t] = cb * se_rsqrt(cb);
+                            *wp = cb * se_rsqrt(cb);
                         }
+                        wp += mstep;
                     } else if (t < a.nframe && !(k == 16 && p != 0)) {
                         const float ca = fmaxf(pw, SE_MRSTFT_CLAMP);
                         const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
@@ -653,6 +686,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         const bool live = (t >= 0 && t < a.nframe);
         const int tc = live ? t : 0;
         const float* mrow = a.refmag + (size_t)row * G::F * a.nframe + tc;
+        const size_t mstep = (size_t)G::S * a.nframe;
         fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
         __syncthreads();
         // |B| for the first task is requested before the passes so its (L2 / DRAM) latency hides behind them;
@@ -660,10 +694,14 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         float mnext[17];
         {
             const int p = unit;
+            const float* pa = mrow + (size_t)task_qa<G>(p) * a.nframe;
+            const float* pb = mrow + (size_t)task_qb<G>(p) * a.nframe;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                mnext[k] = __ldg(mrow + (size_t)(task_qa<G>(p) + G::S * k) * a.nframe);
-                mnext[8 + k] = __ldg(mrow + (size_t)(task_qb<G>(p) + G::S * k) * a.nframe);
+                mnext[k] = __ldg(pa);
+                mnext[8 + k] = __ldg(pb);
+                pa += mstep;
+                pb += mstep;
             }
             mnext[16] = __ldg(mrow + (size_t)G::M * a.nframe);
         }
@@ -676,10 +714,14 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
             for (int k = 0; k < 17; ++k) mb[k] = mnext[k];
             if (i + 1 < G::TC) {
                 const int pn = p + G::NU;
+                const float* pa = mrow + (size_t)task_qa<G>(pn) * a.nframe;
+                const float* pb = mrow + (size_t)task_qb<G>(pn) * a.nframe;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    mnext[k] = __ldg(mrow + (size_t)(task_qa<G>(pn) + G::S * k) * a.nframe);
-                    mnext[8 + k] = __ldg(mrow + (size_t)(task_qb<G>(pn) + G::S * k) * a.nframe);
+                    mnext[k] = __ldg(pa);
+                    mnext[8 + k] = __ldg(pb);
+                    pa += mstep;
+                    pb += mstep;
                 }
             }
             float2 xa[8], xb[8], nyq;
