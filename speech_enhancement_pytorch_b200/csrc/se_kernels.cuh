@@ -685,6 +685,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         const int t = f_base + fr;
         const bool live = (t >= 0 && t < a.nframe);
         const int tc = live ? t : 0;
+        const float alpha_l = live ? alpha : 0.f, beta_l = live ? beta : 0.f;
         const float* mrow = a.refmag + (size_t)row * G::F * a.nframe + tc;
         const size_t mstep = (size_t)G::S * a.nframe;
         fill_stage<G, LOAD_REFLECT>(iobuf, a.est + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
@@ -730,13 +731,13 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
             for (int k = 0; k < 17; ++k) {
                 float2 v = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
                 const float pa = v.x * v.x + v.y * v.y;
-                float coef = 0.f;
-                if (live && pa >= SE_MRSTFT_CLAMP && !(k == 16 && p != 0)) {
-                    const float ia = se_rsqrt(pa);
-                    const float ma = pa * ia;
-                    const float sg = ma > mb[k] ? 1.f : (ma < mb[k] ? -1.f : 0.f);
-                    coef = alpha * (ma - mb[k]) * ia + beta * sg * ia * ia;
-                }
+                // branch-free: below the clamp the magnitude is constant (zero gradient), dead frames carry
+                // zero weights (alpha_l, beta_l), and only p == 0 owns the Nyquist slot
+                const float ia = se_rsqrt(fmaxf(pa, SE_MRSTFT_CLAMP));
+                const float ma = pa * ia;
+                const float sg = ma > mb[k] ? 1.f : (ma < mb[k] ? -1.f : 0.f);
+                float coef = alpha_l * (ma - mb[k]) * ia + beta_l * sg * ia * ia;
+                if (pa < SE_MRSTFT_CLAMP || (k == 16 && p != 0)) coef = 0.f;
                 // edge bins enter the C2R with weight 2 (H = G / c_k, the 1/2 sits in the window)
                 if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;
                 v = make_float2(v.x * coef, v.y * coef);
