@@ -1,7 +1,17 @@
 // se_api_loss.cu -- multi-resolution STFT loss entry points.
 #include "se_host.h"
 
+#include <cstdlib>
+
 using namespace se;
+
+// Default: the forward pass saves the estimate's spectrum (8 bytes per bin per resolution, 12 S per row) so the
+// backward pass runs one transform per resolution instead of two.  SE_MRSTFT_RECOMPUTE=1 (read once per process)
+// selects the memory-lean mode: nothing but |B| is saved and the backward pass re-transforms the estimate.
+static bool loss_recompute() {
+    static const bool v = [] { const char* e = std::getenv("SE_MRSTFT_RECOMPUTE"); return e && e[0] == '1'; }();
+    return v;
+}
 
 static const int kRes[3][3] = {{512, 128, 512}, {1024, 256, 1024}, {2048, 512, 2048}};
 
@@ -28,6 +38,20 @@ template <class G>
 static cudaError_t run_loss_bwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
     return launch(k_loss_bwd<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ADJ, st, a);
 }
+// tuning knobs for the saved-spectrum backward (read once): launch order of the three resolutions and the
+// n = 2048 geometry (8-frame groups: two 256-thread CTAs per SM instead of one 512-thread CTA)
+static int env_flag(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+static bool loss_bwd_ascending() { static const bool v = env_flag("SE_MRSTFT_BWD_ASCENDING", 0) != 0; return v; }
+static bool loss_bwd_fr8() { static const bool v = env_flag("SE_MRSTFT_BWD_FR8", 0) != 0; return v; }
+
+template <class G>
+static cudaError_t run_loss_bwd_saved(LossArgs a, int64_t rows, cudaStream_t st) {
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR, G::FR < 16 ? 2 : 1);
+    return launch(k_loss_bwd_saved<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::SYNTH_ADJ, st, a);
+}
 
 extern "C" {
 
@@ -38,7 +62,8 @@ static int loss_fwd_plan(int64_t rows, int64_t nsample, int r, int& gpc, int& nc
     return (int)(rows * nchunks);
 }
 
-// workspace layout: [per-CTA partial sums (double) for the 3 resolutions | |B| per resolution (float)]
+// workspace layout: [per-CTA partial sums (double) for the 3 resolutions | |B| per resolution (float) |
+//                    A per resolution (float2, absent in recompute mode)]
 static int64_t loss_partials_bytes(int64_t rows, int64_t nsample) {
     int64_t total = 0;
     for (int r = 0; r < 3; ++r) {
@@ -51,9 +76,21 @@ static int64_t loss_refmag_floats(int64_t rows, int64_t nsample, int r) {
     return rows * (kRes[r][0] / 2 + 1) * (1 + nsample / kRes[r][1]);
 }
 
+// bins of resolutions 0..r-1 (r = 3: of all three)
+static int64_t loss_bins_before(int64_t rows, int64_t nsample, int r) {
+    int64_t total = 0;
+    for (int q = 0; q < r; ++q) total += loss_refmag_floats(rows, nsample, q);
+    return total;
+}
+// the |B| region, padded so that the float2 region behind it stays 16-byte aligned
+static int64_t loss_refmag_region_floats(int64_t rows, int64_t nsample) {
+    return (loss_bins_before(rows, nsample, 3) + 3) / 4 * 4;
+}
+
 int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample) {
     int64_t total = loss_partials_bytes(rows, nsample);
-    for (int r = 0; r < 3; ++r) total += loss_refmag_floats(rows, nsample, r) * (int64_t)sizeof(float);
+    total += loss_refmag_region_floats(rows, nsample) * (int64_t)sizeof(float);
+    if (!loss_recompute()) total += loss_bins_before(rows, nsample, 3) * (int64_t)sizeof(float2);
     return total;
 }
 
@@ -75,8 +112,11 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
         if (int rc = get_tables(n, hop, win, false, 0.5f, a.tb)) return rc;
         double* part = part0;
         float* refmag = refmag0;
-        for (int q = 0; q < r; ++q) { part += (size_t)nres[q] * 3; refmag += loss_refmag_floats(rows, nsample, q); }
+        for (int q = 0; q < r; ++q) part += (size_t)nres[q] * 3;
+        refmag += loss_bins_before(rows, nsample, r);
         a.est = est; a.ref = ref; a.partials = part; a.refmag = refmag;
+        a.estspec = loss_recompute() ? nullptr
+                                     : reinterpret_cast<float2*>(refmag0 + loss_refmag_region_floats(rows, nsample)) + loss_bins_before(rows, nsample, r);
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
         a.gpc = gpcs[r]; a.nchunks = nchs[r];
         a.chained = r != 2;
@@ -106,25 +146,33 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
     const float* refmag0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + loss_partials_bytes(rows, nsample));
     for (int r = 0; r < 3; ++r)
         if (int rc = check_common(rows, nsample, kRes[r][0], kRes[r][1], kRes[r][2])) return rc;
-    // largest transform first; followers start in the previous kernel's tail and wait only before they
+    // largest transform first (default); followers start in the previous kernel's tail and wait only before they
     // accumulate into g_est (see k_loss_bwd)
-    for (int r = 2; r >= 0; --r) {
+    const bool asc = !loss_recompute() && loss_bwd_ascending();
+    for (int idx = 0; idx < 3; ++idx) {
+        const int r = asc ? idx : 2 - idx;
         const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
         LossArgs a{};
         if (int rc = get_tables(n, hop, win, false, 0.5f, a.tb)) return rc;
-        const float* refmag = refmag0;
-        for (int q = 0; q < r; ++q) refmag += loss_refmag_floats(rows, nsample, q);
+        const float* refmag = refmag0 + loss_bins_before(rows, nsample, r);
         a.est = est; a.refmag = const_cast<float*>(refmag); a.g_est = g_est; a.sums = sums + 3 * r; a.gout = gout;
         a.nsample = (int)nsample; a.nframe = (int)(1 + nsample / hop);
         a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
-        a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
-                              : plan_synthesis(rows, a.b_hi, n / hop, 2, 16);
-        a.accumulate = r != 2;
-        a.chained = r != 2;
+        a.accumulate = idx != 0;
+        a.chained = idx != 0;
         a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
         a.inv_res = 1.0f / 3.0f;
         cudaError_t e;
-        SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd<G>(a, rows, (cudaStream_t)stream)));
+        if (loss_recompute()) {
+            a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
+                                  : plan_synthesis(rows, a.b_hi, n / hop, 2, 16);
+            SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd<G>(a, rows, (cudaStream_t)stream)));
+        } else {
+            a.estspec = const_cast<float2*>(reinterpret_cast<const float2*>(refmag0 + loss_refmag_region_floats(rows, nsample))) +
+                        loss_bins_before(rows, nsample, r);
+            if (n == 2048 && loss_bwd_fr8()) e = run_loss_bwd_saved<Geo<2048, 512, 256, 8>>(a, rows, (cudaStream_t)stream);
+            else SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd_saved<G>(a, rows, (cudaStream_t)stream)));
+        }
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_bwd launch");
     }
     return 0;

@@ -558,6 +558,7 @@ struct LossArgs {
     float* g_est;            // bwd
     double* partials;        // fwd: [grid][3]
     float* refmag;           // fwd writes / bwd reads |B| (clamped) as [rows][F][T] for this resolution
+    float2* estspec;         // fwd writes / bwd reads the estimate's spectrum A as [rows][F][T] (nullptr: recompute mode)
     const double* sums;      // bwd: this resolution's 3 sums
     const float* gout;       // bwd: device scalar
     int nsample, nframe;
@@ -629,6 +630,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
                         s_lm += 0.34657359f * fabsf(se_log2(cb) - se_log2(ca));
                     }
                 }
+                // keep A for the backward pass: it then runs one transform (the adjoint) instead of two
+                if (sig == 1 && a.estspec)
+                    store_task_ft2<G>(a.estspec + (size_t)row * G::F * a.nframe, a.nframe, t, p, xa, xb, nyq, 1.0f);
             }
         }
     }
@@ -751,6 +755,91 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
         __syncthreads();
     }
     if (c.last) {
+        finish_adj<G>(hold, gx_row, a.nsample, a.accumulate, 1.0f, tid);
+    }
+}
+
+// Backward from the spectrum the forward pass saved: load A and |B| per bin, form G = coef * A in registers and
+// run the STFT adjoint (synthesis + reflect fold).  One transform per resolution instead of two, at the price
+// of 12 bytes per bin of scratch (HBM is 180 GB; the recompute kernel above stays as the memory-lean mode).
+template <class G>
+__global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd_saved(const LossArgs a) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    float* hold = reinterpret_cast<float*>(se_smem + Smem<G>::ZB + Smem<G>::OSTAGE);
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
+    if (a.chained) pdl_launch_dependents();
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::OSTAGE + Smem<G>::HOLD, tid);
+    __syncthreads();
+    if (!a.chained) { pdl_wait(); pdl_launch_dependents(); }
+    bool must_wait = a.chained != 0;
+    const int row = blockIdx.x / a.nchunks, chunk = blockIdx.x - row * a.nchunks;
+    const Chunk c = make_chunk<G>(chunk, a.nchunks, a.b_lo, a.b_hi);
+    const double d2 = a.sums[0], b2 = a.sums[1];
+    const float gs = __ldg(a.gout) * a.inv_res;
+    const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
+    const float beta = gs * a.inv_count;
+    float* gx_row = a.g_est + (size_t)row * a.nsample;
+    const size_t rbase = (size_t)row * G::F * a.nframe;
+    const size_t step = (size_t)G::S * a.nframe;
+    float2 carry[G::TA][G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i)
+#pragma unroll
+        for (int s = 0; s < G::SEG; ++s) carry[i][s] = make_float2(0.f, 0.f);
+    for (int g = 0; g < c.ngroups; ++g) {
+        const int f_base = c.f0 + g * G::FR;
+        const int t = f_base + fr;
+        const bool live = (t >= 0 && t < a.nframe);
+        const int tc = live ? t : 0;                       // clamped: loads stay in bounds, weights zeroed
+        const float alpha_l = live ? alpha : 0.f, beta_l = live ? beta : 0.f;
+        const float2* srow = a.estspec + rbase + tc;
+        const float* mrow = a.refmag + rbase + tc;
+        SE_TC_PRAGMA
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 ya[8], yb[8], nyq = make_float2(0.f, 0.f);
+            float ma[8], mb[8], mn = 1.f;
+            {
+                const size_t ia = (size_t)task_qa<G>(p) * a.nframe, ib = (size_t)task_qb<G>(p) * a.nframe;
+                const float2* sa = srow + ia;
+                const float2* sb = srow + ib;
+                const float* pa = mrow + ia;
+                const float* pb = mrow + ib;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    ya[k] = __ldg(sa); yb[k] = __ldg(sb);
+                    ma[k] = __ldg(pa); mb[k] = __ldg(pb);
+                    sa += step; sb += step; pa += step; pb += step;
+                }
+                if (p == 0) {
+                    nyq = __ldg(srow + (size_t)G::M * a.nframe);
+                    mn = __ldg(mrow + (size_t)G::M * a.nframe);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 17; ++k) {
+                float2 v = k < 8 ? ya[k] : (k < 16 ? yb[k - 8] : nyq);
+                const float m = k < 8 ? ma[k] : (k < 16 ? mb[k - 8] : mn);
+                const float pw = v.x * v.x + v.y * v.y;
+                const float ia = se_rsqrt(fmaxf(pw, SE_MRSTFT_CLAMP));
+                const float mag = pw * ia;
+                const float sg = mag > m ? 1.f : (mag < m ? -1.f : 0.f);
+                float coef = alpha_l * (mag - m) * ia + beta_l * sg * ia * ia;
+                if (pw < SE_MRSTFT_CLAMP || (k == 16 && p != 0)) coef = 0.f;
+                if (p == 0 && (k == 0 || k == 16)) coef *= 2.f;     // edge bins enter the C2R with weight 2
+                v = make_float2(v.x * coef, v.y * coef);
+                if (k < 8) ya[k] = v; else if (k < 16) yb[k - 8] = v; else nyq = v;
+            }
+            synthesis_task<G>(zb, tb, p, fr, ya, yb, nyq);
+        }
+        synthesis_tail<G>(zb, tb, ostage, unit, fr, carry);
+        if (must_wait) { pdl_wait(); must_wait = false; }
+        emit_adj<G>(ostage, hold, gx_row, f_base, c, a.nsample, a.accumulate, 1.0f, tid);
+    }
+    if (c.last) {
+        __syncthreads();
         finish_adj<G>(hold, gx_row, a.nsample, a.accumulate, 1.0f, tid);
     }
 }

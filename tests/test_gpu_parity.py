@@ -195,6 +195,41 @@ def test_mrstft_loss_and_gradient(se, oref, shape):
     directional_check(grad, g64, 2.0 * g_ref)
 
 
+_MODE_SCRIPT = """
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+import speech_enhancement_pytorch_b200 as se
+g = torch.Generator().manual_seed(4242)
+ref = torch.randn(5, 1, 20000, generator=g)
+est = (ref + 0.2 * torch.randn(5, 1, 20000, generator=g)).cuda().requires_grad_(True)
+loss = se.loss_mrstft(est, ref.cuda())
+(grad,) = torch.autograd.grad(loss, est)
+np.savez({out!r}, loss=float(loss), grad=grad.cpu().numpy())
+"""
+
+
+@pytest.mark.parametrize("env", [{"SE_MRSTFT_RECOMPUTE": "1"}, {"SE_MRSTFT_BWD_FR8": "1"}, {"SE_MRSTFT_BWD_ASCENDING": "1"},
+                                 {"SE_FORCE_GROUPS": "3"}])
+def test_mrstft_loss_modes_agree(se, tmp_path, env):
+    """The saved-spectrum backward (default), the memory-lean recompute mode and the tuning knobs are the same
+    function: each runs in its own process (the switches are read once) and must reproduce the default."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "mode.npz")
+    subprocess.run([sys.executable, "-c", _MODE_SCRIPT.format(root=root, out=out)], check=True, env={**os.environ, **env},
+                   timeout=600)
+    got = np.load(out)
+    g = torch.Generator().manual_seed(4242)
+    ref = torch.randn(5, 1, 20000, generator=g)
+    est = (ref + 0.2 * torch.randn(5, 1, 20000, generator=g)).cuda().requires_grad_(True)
+    loss = se.loss_mrstft(est, ref.cuda())
+    (grad,) = torch.autograd.grad(loss, est)
+    assert abs(float(got["loss"]) - float(loss)) <= 1e-6 * abs(float(loss))
+    assert rel(torch.from_numpy(got["grad"]), grad) < 2e-5
+
+
 def test_mrstft_full_size_survey_value(se):
     """seed 1236, est = ref + 0.1 N(0,1), 128x1x64000 -> loss 0.168027."""
     g = torch.Generator().manual_seed(1236)
