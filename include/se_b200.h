@@ -103,6 +103,9 @@ int se_mask_bwd(const float* spec, const float* mask, const float* gout, float* 
  *           workspace: se_mrstft_workspace_bytes(rows, nsample) bytes of device scratch; the
  *           forward pass also leaves the clamped reference magnitudes |B| there, so the backward
  *           pass transforms only the estimate.  Keep it alive (unmodified) until bwd has run.
+ *           With SE_MRSTFT_SAVE_SPECTRUM=1 in the environment (read once per process) the forward
+ *           pass also saves the estimate's spectrum (3x the workspace) and the backward pass runs
+ *           one transform per resolution instead of two; same results, same signatures.
  *   value : sums (after the caller all-reduced them across ranks) -> loss (device float).
  *           global_rows = rows summed over ranks (sets the mean's denominator).
  *   bwd   : g_est [rows,N] = gout * dloss/dest, gout a DEVICE scalar (upstream gradient);

@@ -5,11 +5,12 @@
 
 using namespace se;
 
-// Default: the forward pass saves the estimate's spectrum (8 bytes per bin per resolution, 12 S per row) so the
-// backward pass runs one transform per resolution instead of two.  SE_MRSTFT_RECOMPUTE=1 (read once per process)
-// selects the memory-lean mode: nothing but |B| is saved and the backward pass re-transforms the estimate.
+// Default: only |B| is saved by the forward pass and the backward pass re-transforms the estimate.
+// SE_MRSTFT_SAVE_SPECTRUM=1 (read once per process) makes the forward pass also save the estimate's spectrum
+// (8 bytes per bin per resolution, 3x the workspace) so that the backward pass runs one transform per resolution
+// instead of two -- a measured wash on B200 (see k_loss_bwd_saved), kept as an alternative for compute-poorer parts.
 static bool loss_recompute() {
-    static const bool v = [] { const char* e = std::getenv("SE_MRSTFT_RECOMPUTE"); return e && e[0] == '1'; }();
+    static const bool v = [] { const char* e = std::getenv("SE_MRSTFT_SAVE_SPECTRUM"); return !(e && e[0] == '1'); }();
     return v;
 }
 
@@ -38,18 +39,9 @@ template <class G>
 static cudaError_t run_loss_bwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
     return launch(k_loss_bwd<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ADJ, st, a);
 }
-// tuning knobs for the saved-spectrum backward (read once): launch order of the three resolutions and the
-// n = 2048 geometry (8-frame groups: two 256-thread CTAs per SM instead of one 512-thread CTA)
-static int env_flag(const char* name, int dflt) {
-    const char* e = std::getenv(name);
-    return e ? std::atoi(e) : dflt;
-}
-static bool loss_bwd_ascending() { static const bool v = env_flag("SE_MRSTFT_BWD_ASCENDING", 0) != 0; return v; }
-static bool loss_bwd_fr8() { static const bool v = env_flag("SE_MRSTFT_BWD_FR8", 0) != 0; return v; }
-
 template <class G>
 static cudaError_t run_loss_bwd_saved(LossArgs a, int64_t rows, cudaStream_t st) {
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR, G::FR < 16 ? 2 : 1);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR);
     return launch(k_loss_bwd_saved<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::SYNTH_ADJ, st, a);
 }
 
@@ -146,9 +138,10 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
     const float* refmag0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + loss_partials_bytes(rows, nsample));
     for (int r = 0; r < 3; ++r)
         if (int rc = check_common(rows, nsample, kRes[r][0], kRes[r][1], kRes[r][2])) return rc;
-    // largest transform first (default); followers start in the previous kernel's tail and wait only before they
-    // accumulate into g_est (see k_loss_bwd)
-    const bool asc = !loss_recompute() && loss_bwd_ascending();
+    // largest transform first; followers start in the previous kernel's tail and wait only before they accumulate
+    // into g_est (see k_loss_bwd).  Saved-spectrum mode goes smallest first: the forward pass wrote that scratch
+    // last, so part of it is still in L2 (measured 211 -> 205 us).
+    const bool asc = !loss_recompute();
     for (int idx = 0; idx < 3; ++idx) {
         const int r = asc ? idx : 2 - idx;
         const int n = kRes[r][0], hop = kRes[r][1], win = kRes[r][2];
@@ -170,8 +163,7 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
         } else {
             a.estspec = const_cast<float2*>(reinterpret_cast<const float2*>(refmag0 + loss_refmag_region_floats(rows, nsample))) +
                         loss_bins_before(rows, nsample, r);
-            if (n == 2048 && loss_bwd_fr8()) e = run_loss_bwd_saved<Geo<2048, 512, 256, 8>>(a, rows, (cudaStream_t)stream);
-            else SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd_saved<G>(a, rows, (cudaStream_t)stream)));
+            SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd_saved<G>(a, rows, (cudaStream_t)stream)));
         }
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_bwd launch");
     }

@@ -146,13 +146,13 @@ void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_p
 // Pick the groups-per-chunk g that minimises (waves x g): a chunk of g groups emits 16 g - (ola-1)
 // blocks (the first ola-1 frames are halo recompute), so larger g wastes less, but the grid must still
 // fill the GPU in whole waves.  ctas_per_sm = resident CTAs of this kernel per SM.
-int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group, int min_groups) {
+int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group) {
     const int64_t slots = 148LL * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     int best_chunks = 1;
     double best_cost = 1e30;
     // SE_FORCE_GROUPS=g pins the choice (tests exercise the multi-group carry path on tiny inputs)
     const char* force = std::getenv("SE_FORCE_GROUPS");
-    const int g_lo = force ? std::atoi(force) : (min_groups > 1 ? min_groups : 1), g_hi = force ? std::atoi(force) : 8;
+    const int g_lo = force ? std::atoi(force) : 1, g_hi = force ? std::atoi(force) : 8;
     for (int g = (g_lo < 1 ? 1 : g_lo); g <= (g_hi > 8 ? 8 : g_hi); ++g) {
         const int cb_max = frames_per_group * g - (ola - 1);
         const int nchunks = (nb + cb_max - 1) / cb_max;

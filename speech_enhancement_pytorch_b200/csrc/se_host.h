@@ -16,9 +16,7 @@ int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out
 // torch.istft's "window overlap add min" check on the host (no device sync)
 bool envelope_ok(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_);
 void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_per_group);
-// min_groups: the reflect-fold zone at the end of a row (n + hop samples) must lie inside ONE chunk, so 8-frame
-// geometries need at least two groups per chunk
-int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group, int min_groups = 1);
+int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group);
 int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length);
 
 // MODE (0..3) x TANH -> compile-time template arguments

@@ -631,8 +631,16 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
                     }
                 }
                 // keep A for the backward pass: it then runs one transform (the adjoint) instead of two
-                if (sig == 1 && a.estspec)
-                    store_task_ft2<G>(a.estspec + (size_t)row * G::F * a.nframe, a.nframe, t, p, xa, xb, nyq, 1.0f);
+                if (sig == 1 && a.estspec && t < a.nframe) {
+                    float2* srow = a.estspec + (size_t)row * G::F * a.nframe + t;
+                    float2* sa = srow + (size_t)task_qa<G>(p) * a.nframe;
+                    float2* sb = srow + (size_t)task_qb<G>(p) * a.nframe;
+                    // evict-first stores: written once, read once much later -- keeps the scratch from displacing
+                    // the step's reusable lines in L2 (measured: loss fwd 191 -> 184 us)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { se_store_stream(sa, xa[k]); se_store_stream(sb, xb[k]); sa += mstep; sb += mstep; }
+                    if (p == 0) se_store_stream(srow + (size_t)G::M * a.nframe, nyq);
+                }
             }
         }
     }
@@ -759,9 +767,12 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     }
 }
 
-// Backward from the spectrum the forward pass saved: load A and |B| per bin, form G = coef * A in registers and
-// run the STFT adjoint (synthesis + reflect fold).  One transform per resolution instead of two, at the price
-// of 12 bytes per bin of scratch (HBM is 180 GB; the recompute kernel above stays as the memory-lean mode).
+// Backward from a spectrum saved by the forward pass (opt-in, SE_MRSTFT_SAVE_SPECTRUM=1): load A and |B| per bin, form
+// G = coef * A in registers and run the STFT adjoint (synthesis + reflect fold).  One transform per resolution
+// instead of two, at the price of 8 more bytes per bin of scratch written and read back through DRAM (300 MB per
+// 64 x 4 s step, more than L2 holds).  Measured on B200 it is a wash (step 567-575 us against 571-575 us for the
+// recompute kernel above: the forward pays 26-33 us for the stores, the backward gains 14-20 us), so recompute,
+// with a third of the workspace, stays the default; profiles/r01_notes.md has the table.
 template <class G>
 __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd_saved(const LossArgs a) {
     SE_SMEM_DECL;

@@ -71,6 +71,17 @@ __device__ __forceinline__ float se_log2(float x) {
 #endif
 }
 
+// Evict-first store for scratch that is written once and read once, much later (the loss workspace): keeps it from
+// displacing the step's reusable lines in L2.
+template <class T>
+__device__ __forceinline__ void se_store_stream(T* p, T v) {
+#ifdef SE_EMULATE
+    *p = v;
+#else
+    __stcs(p, v);
+#endif
+}
+
 // pdl = true: the kernel may start while its stream predecessor is still running (it must call
 // pdl_wait() before touching the predecessor's output); pdl = false: classic stream serialisation.
 template <class... Params, class... Args>

@@ -208,10 +208,10 @@ np.savez({out!r}, loss=float(loss), grad=grad.cpu().numpy())
 """
 
 
-@pytest.mark.parametrize("env", [{"SE_MRSTFT_RECOMPUTE": "1"}, {"SE_MRSTFT_BWD_FR8": "1"}, {"SE_MRSTFT_BWD_ASCENDING": "1"},
+@pytest.mark.parametrize("env", [{"SE_MRSTFT_SAVE_SPECTRUM": "1"}, {"SE_MRSTFT_SAVE_SPECTRUM": "1", "SE_FORCE_GROUPS": "3"},
                                  {"SE_FORCE_GROUPS": "3"}])
 def test_mrstft_loss_modes_agree(se, tmp_path, env):
-    """The saved-spectrum backward (default), the memory-lean recompute mode and the tuning knobs are the same
+    """The recompute backward (default), the opt-in saved-spectrum mode and forced multi-group chunking are the same
     function: each runs in its own process (the switches are read once) and must reproduce the default."""
     import os
     import subprocess
