@@ -51,6 +51,7 @@ def workload_config(args, world):
                         f"{args.rows}x{args.nsample / SR:g} s @16 kHz per GPU, MR-STFT loss 512/1024/2048, fwd+bwd to the raw mask",
             "rows_per_gpu": args.rows, "nsample": args.nsample, "n_fft": N_FFT, "hop": HOP,
             "global_rows": args.rows * world, "parallelism": f"utterance-sharded x{world}",
+            "exchange": "none (1 GPU)" if world == 1 else os.environ.get("_SE_BENCH_EXCHANGE", "?"),
             "l2": "working set ~400 MB/step > 126 MB L2; inputs rotate over 2 buffer sets"}
 
 
@@ -179,6 +180,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     L = nv.lib()
+    # the path's one exchange step: fused peer-memory kernel (exchange + loss value) when the ranks can map each
+    # other's buffers, else NCCL all-reduce followed by the value kernel
+    px = None
+    if group is not None:
+        from speech_enhancement_pytorch_b200 import distributed as sed
+        px = sed.peer_exchange(group, dev)
+    os.environ["_SE_BENCH_EXCHANGE"] = ("9 doubles, one fused peer-memory kernel over NVLink (se_mrstft_exchange_value)" if px is not None
+                                        else "9 doubles, NCCL all-reduce on the compute stream")
     rows, N = args.rows, args.nsample
     F, T = N_FFT // 2 + 1, 1 + N // HOP
     # three compositions of the same step, all timed and reported; the first is the default:
@@ -233,9 +242,12 @@ def run_ours(args):
         else:
             k_stft(x); k_mask(raw); k_istft()
         k_loss_fwd(clean)
-        if group is not None:
-            dist.all_reduce(sums, group=group)          # the path's only exchange step
-        k_loss_val()
+        if px is not None:
+            px.exchange_value(sums, rows * world, N, loss, st)   # the path's only exchange step, fused with the value
+        else:
+            if group is not None:
+                dist.all_reduce(sums, group=group)
+            k_loss_val()
         k_loss_bwd(clean)
         if comp == "fused":
             k_enh_bwd(x, raw)

@@ -117,6 +117,24 @@ int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsampl
 int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* sums, const float* gout,
                        int64_t global_rows, int64_t rows, int64_t nsample, float* g_est, void* stream);
 
+/* ---- the exchange step of the utterance-sharded MR-STFT loss over NVLink peer memory (SURVEY.md 8e;
+ * the reference has no counterpart: its multi-GPU path is nn.DataParallel, src/solver.py:144-145).
+ * One process per GPU.  se_p2p_create allocates this rank's exchange buffer on the current device and
+ * returns its 64-byte cudaIpc handle; the host side gathers the handles (torch.distributed) and maps
+ * every peer's buffer with se_p2p_open.  se_mrstft_exchange_value then replaces "ncclAllReduce(sums)
+ * followed by se_mrstft_loss_value" with ONE single-CTA kernel on `stream`: it stores this rank's 9
+ * sums into every peer's buffer, waits (on the device) until all ranks' sums have arrived, adds them in
+ * rank order -- every rank gets the same bits -- and writes the global sums in place and, if loss !=
+ * NULL, the loss.  bufs is a HOST array of `world` device pointers, bufs[rank] the local buffer.
+ * Every rank of the group must make the call the same number of times; a peer that does not show up
+ * within ~10 s traps the kernel (the stream reports a CUDA error) instead of hanging. */
+int se_p2p_create(void** local, unsigned char* handle64);
+int se_p2p_open(const unsigned char* handle64, void** peer);
+int se_p2p_close(void* peer);
+int se_p2p_destroy(void* local);
+int se_mrstft_exchange_value(double* sums, void* const* bufs, int world, int rank, int64_t global_rows,
+                             int64_t nsample, float* loss, void* stream);
+
 /* ---- STFT-domain training losses against a WAVEFORM target: what
  * loss_function(enhanced, stft_custom(sources)) computes with torch's mse_loss / l1_loss on
  * [B,C,F,T,2] (src/solver.py:457-458,480; src/distrib.py:263-267), without materialising the target

@@ -33,6 +33,108 @@ def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
     return sums
 
 
+class PeerExchange:
+    """This rank's view of the peer-memory exchange buffers of a process group (csrc/se_api_p2p.cu).
+
+    `exchange_value` is the fused replacement of `all_reduce_sums` + `se_mrstft_loss_value`: one single-CTA kernel on
+    the current stream stores the 9 sums into every peer's buffer over NVLink, waits on the device for all ranks,
+    adds in rank order and writes the global sums (in place) and the loss."""
+
+    def __init__(self, group, device):
+        import ctypes
+        import socket
+        import torch.distributed as dist
+        from . import _native as nv
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise NotImplementedError("peer exchange supports up to 16 ranks")
+        self.device = torch.device(device)
+        L = nv.lib()
+        local = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        self.local, self.peers, err = None, [], None
+        try:
+            with nv.on_device(self.device):
+                nv.check(L.se_p2p_create(ctypes.byref(local), handle))
+            self.local = local.value
+        except Exception as e:                     # still take part in the gather below, then fail with everyone
+            err = e
+        infos = [None] * self.world
+        dist.all_gather_object(infos, (socket.gethostname(), handle.raw if err is None else None), group=group)
+        ptrs = (ctypes.c_void_p * self.world)()
+        try:
+            if err is not None:
+                raise err
+            if any(raw is None for _, raw in infos):
+                raise NotImplementedError("a rank of the group could not create its exchange buffer")
+            if len({h for h, _ in infos}) != 1:
+                raise NotImplementedError("peer exchange needs all ranks of the group on one node")
+            for r, (_, raw) in enumerate(infos):
+                if r == self.rank:
+                    ptrs[r] = self.local
+                    continue
+                peer = ctypes.c_void_p()
+                with nv.on_device(self.device):
+                    nv.check(L.se_p2p_open(raw, ctypes.byref(peer)))
+                self.peers.append(peer.value)
+                ptrs[r] = peer.value
+        except Exception:
+            self.close()
+            raise
+        self.ptrs = ptrs
+
+    def exchange_value(self, sums: torch.Tensor, global_rows: int, nsample: int, loss, stream: int):
+        from . import _native as nv
+        if sums.dtype != torch.float64 or sums.numel() != 9 or sums.device != self.device:
+            raise ValueError("expected the 9 float64 MR-STFT partial sums on this exchange's device")
+        nv.check(nv.lib().se_mrstft_exchange_value(sums.data_ptr(), self.ptrs, self.world, self.rank, global_rows, nsample,
+                                                   loss.data_ptr() if loss is not None else None, stream))
+
+    def close(self):
+        from . import _native as nv
+        L = nv.lib()
+        with nv.on_device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self.peers:
+                L.se_p2p_close(p)
+            self.peers = []
+            if self.local:
+                L.se_p2p_destroy(self.local)
+                self.local = None
+
+
+_exchanges = {}
+
+
+def peer_exchange(group, device):
+    """The group's PeerExchange on `device`, created on first use (a collective call: every rank of the group must
+    reach it).  Returns None -- and the caller uses NCCL -- when SE_P2P_EXCHANGE=0, when the ranks are not all on one
+    node, or when any rank could not map its peers; the decision is taken jointly so that all ranks agree."""
+    import os
+    import torch.distributed as dist
+    key = (id(group), torch.device(device).index)
+    if key in _exchanges:
+        return _exchanges[key]
+    px, ok = None, os.environ.get("SE_P2P_EXCHANGE", "1") != "0"
+    if ok:
+        try:
+            px = PeerExchange(group, device)
+        except NotImplementedError:
+            ok = False
+        except Exception as e:                     # e.g. no peer access between two of the GPUs
+            import warnings
+            warnings.warn(f"peer exchange unavailable on rank {dist.get_rank(group)} ({e}); using NCCL")
+            ok = False
+    flags = [None] * dist.get_world_size(group)
+    dist.all_gather_object(flags, ok, group=group)
+    if not all(flags):
+        if px is not None:
+            px.close()
+        px = None
+    _exchanges[key] = px
+    return px
+
+
 def loss_from_sums(sums, global_rows: int, nsample: int) -> float:
     """Host restatement of se_mrstft_loss_value (csrc/se_kernels.cuh k_loss_value)."""
     total = 0.0

@@ -164,13 +164,20 @@ class _MRSTFT(torch.autograd.Function):
         with nv.on_device(est.device):
             st = nv.stream_ptr(est.device)
             nv.check(L.se_mrstft_loss_fwd(est.data_ptr(), ref.data_ptr(), rows, n, sums.data_ptr(), ws.data_ptr(), st))
+            px = None
             if group is not None:
                 import torch.distributed as dist
+                from . import distributed as sed
                 # the one exchange step of the path: 9 partial sums, no host sync.
                 # Utterance sharding gives every rank the same row count unless told otherwise.
-                dist.all_reduce(sums, group=group)
                 global_rows = global_rows_hint or rows * dist.get_world_size(group)
-            nv.check(L.se_mrstft_loss_value(sums.data_ptr(), global_rows, n, loss.data_ptr(), st))
+                px = sed.peer_exchange(group, est.device)
+                if px is None:
+                    dist.all_reduce(sums, group=group)      # NCCL: multi-node groups, or no peer access
+            if px is not None:
+                px.exchange_value(sums, global_rows, n, loss, st)   # exchange + value in one kernel over peer memory
+            else:
+                nv.check(L.se_mrstft_loss_value(sums.data_ptr(), global_rows, n, loss.data_ptr(), st))
         ctx.save_for_backward(est, ws, sums)
         ctx.global_rows = global_rows
         return loss
