@@ -46,12 +46,12 @@ def parse():
     return ap.parse_args()
 
 
-def workload_config(args, world):
+def workload_config(args, world, exchange="none (1 GPU)"):
     return {"workload": f"cfg2: DCUnet 'E' complex-ratio mask, n_fft={N_FFT} hop={HOP} Hann, "
                         f"{args.rows}x{args.nsample / SR:g} s @16 kHz per GPU, MR-STFT loss 512/1024/2048, fwd+bwd to the raw mask",
             "rows_per_gpu": args.rows, "nsample": args.nsample, "n_fft": N_FFT, "hop": HOP,
             "global_rows": args.rows * world, "parallelism": f"utterance-sharded x{world}",
-            "exchange": "none (1 GPU)" if world == 1 else os.environ.get("_SE_BENCH_EXCHANGE", "?"),
+            "exchange": exchange,
             "l2": "working set ~400 MB/step > 126 MB L2; inputs rotate over 2 buffer sets"}
 
 
@@ -186,8 +186,9 @@ def run_ours(args):
     if group is not None:
         from speech_enhancement_pytorch_b200 import distributed as sed
         px = sed.peer_exchange(group, dev)
-    os.environ["_SE_BENCH_EXCHANGE"] = ("9 doubles, one fused peer-memory kernel over NVLink (se_mrstft_exchange_value)" if px is not None
-                                        else "9 doubles, NCCL all-reduce on the compute stream")
+    exchange = ("none (1 GPU)" if group is None else
+                "9 doubles, one fused peer-memory kernel over NVLink (se_mrstft_exchange_value)" if px is not None else
+                "9 doubles, NCCL all-reduce on the compute stream")
     rows, N = args.rows, args.nsample
     F, T = N_FFT // 2 + 1, 1 + N // HOP
     # three compositions of the same step, all timed and reported; the first is the default:
@@ -350,6 +351,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         import types
+        sync_all()          # rank 0 alone ran the per-kernel loops: line the ranks up before the next exchange step
         cfg = types.SimpleNamespace(n_fft=N_FFT, hop_length=HOP, win_length=WIN, center=True)
         hx = [torch.randn(rows, 1, N, generator=g).pin_memory() for _ in range(2)]
         hc = [(hx[i] + 0.3 * torch.randn(rows, 1, N, generator=g)).pin_memory() for i in range(2)]
@@ -516,7 +518,7 @@ def run_ours(args):
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, exchange),
         "clocks": clocks, "e2e": e2e, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
         "composition": comp, "alt_compositions": alts,
         "loss": loss_val, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,

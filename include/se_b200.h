@@ -127,7 +127,7 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
  * rank order -- every rank gets the same bits -- and writes the global sums in place and, if loss !=
  * NULL, the loss.  bufs is a HOST array of `world` device pointers, bufs[rank] the local buffer.
  * Every rank of the group must make the call the same number of times; a peer that does not show up
- * within ~10 s traps the kernel (the stream reports a CUDA error) instead of hanging. */
+ * within ~60 s traps the kernel (the stream reports a CUDA error) instead of hanging. */
 int se_p2p_create(void** local, unsigned char* handle64);
 int se_p2p_open(const unsigned char* handle64, void** peer);
 int se_p2p_close(void* peer);

@@ -160,7 +160,7 @@ int se_mrstft_exchange_value(double* sums, void* const* bufs, int world, int ran
     static const int res[3][2] = {{512, 128}, {1024, 256}, {2048, 512}};
     for (int r = 0; r < 3; ++r) a.cnt[r] = (double)global_rows * (res[r][0] / 2 + 1) * (double)(1 + nsample / res[r][1]);
     a.sums = sums; a.loss = loss; a.world = world; a.rank = rank;
-    a.spin_limit = 20000000000LL;              // ~10 s at 2 GHz
+    a.spin_limit = 120000000000LL;             // ~60 s at 2 GHz: ranks may reach the step seconds apart (rank-0-only work)
     cudaError_t e = launch(k_sums_exchange, 1u, 32u, 0, (cudaStream_t)stream, a);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_exchange_value launch");
 }
