@@ -95,6 +95,15 @@ int se_mask_fwd(const float* spec, const float* mask, float* out, int64_t count,
 int se_mask_bwd(const float* spec, const float* mask, const float* gout, float* gmask, float* gspec,
                 int64_t count, int mode, int pre_tanh, void* stream);
 
+/* ---- the same masks in DCCRN's layout (src/model/dccrn.py:147-223: real = specs[:, :F], imag = specs[:, F:],
+ * masks padded at the DC bin to [B,F,T], out_spec = cat([real, imag], 1)): spec / out / gout / gspec are planar
+ * [rows, 2*nbin, nframe], the masks and their gradients two planes [rows, nbin, nframe].  mode = SE_MASK_E / C / R. */
+int se_mask_planar_fwd(const float* spec, const float* mask_re, const float* mask_im, float* out, int64_t rows,
+                       int64_t nbin, int64_t nframe, int mode, void* stream);
+int se_mask_planar_bwd(const float* spec, const float* mask_re, const float* mask_im, const float* gout,
+                       float* gmask_re, float* gmask_im, float* gspec, int64_t rows, int64_t nbin, int64_t nframe,
+                       int mode, void* stream);
+
 /* ---- multi-resolution STFT loss (new component; calling convention loss_function(enhanced,
  * sources), src/solver.py:480; definition SURVEY.md 8c).  Resolutions are fixed:
  * (512,128,512) (1024,256,1024) (2048,512,2048).

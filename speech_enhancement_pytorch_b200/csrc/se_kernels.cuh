@@ -1077,4 +1077,45 @@ __global__ void __launch_bounds__(256) k_mask_bwd_t(const float2* __restrict__ s
     }
 }
 
+
+// DCCRN layout (src/model/dccrn.py:147-223): spectrum planar [rows][2F][T] (Re bins, then Im bins), masks two planes
+// [rows][F][T].  Same per-bin math as above; no stack / cat copies around it.  plane = F*T elements.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_mask_planar_fwd_t(const float* __restrict__ spec, const float* __restrict__ mre,
+                                                           const float* __restrict__ mim, float* __restrict__ out,
+                                                           int64_t plane, int bpr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    // bpr blocks per row: one 32-bit divide per block instead of a 64-bit divide per element
+    const int64_t row = blockIdx.x / bpr;
+    const int chunk = blockIdx.x - (int)row * bpr;
+    for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < plane; i += (int64_t)bpr * blockDim.x) {
+        const int64_t e = row * plane + i, re = e + row * plane, im = re + plane;  // row*2*plane + i (+ plane)
+        const float2 y = MaskMath::apply<MODE, false>(make_float2(__ldg(spec + re), __ldg(spec + im)),
+                                                      make_float2(__ldg(mre + e), __ldg(mim + e)));
+        out[re] = y.x;
+        out[im] = y.y;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_mask_planar_bwd_t(const float* __restrict__ spec, const float* __restrict__ mre,
+                                                           const float* __restrict__ mim, const float* __restrict__ gout,
+                                                           float* __restrict__ gmre, float* __restrict__ gmim,
+                                                           float* __restrict__ gspec, int64_t plane, int bpr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t row = blockIdx.x / bpr;
+    const int chunk = blockIdx.x - (int)row * bpr;
+    for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < plane; i += (int64_t)bpr * blockDim.x) {
+        const int64_t e = row * plane + i, re = e + row * plane, im = re + plane;
+        float2 gm, gx;
+        MaskMath::grad<MODE, false>(make_float2(__ldg(spec + re), __ldg(spec + im)), make_float2(__ldg(mre + e), __ldg(mim + e)),
+                                    make_float2(__ldg(gout + re), __ldg(gout + im)), gm, gx);
+        gmre[e] = gm.x;
+        gmim[e] = gm.y;
+        if (gspec) { gspec[re] = gx.x; gspec[im] = gx.y; }
+    }
+}
+
 }  // namespace se

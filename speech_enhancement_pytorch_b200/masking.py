@@ -20,12 +20,8 @@ def apply_mask(spec, mask, mode="E", pre_tanh=False):
 
 def apply_mask_dccrn(specs, mask_real, mask_imag, mode="E"):
     """DCCRN layout (dccrn.py:147-223): specs [B,2F,T] (Re bins then Im bins), masks [B,F,T];
-    returns out_spec [B,2F,T]."""
-    nf = specs.shape[1] // 2
-    spec = torch.stack([specs[:, :nf], specs[:, nf:]], dim=-1)
-    mask = torch.stack([mask_real, mask_imag], dim=-1)
-    out = ops.mask_apply(spec, mask, mode, False)
-    return torch.cat([out[..., 0], out[..., 1]], dim=1)
+    returns out_spec [B,2F,T].  One planar kernel each way (se_mask_planar_fwd/bwd): no stack / cat copies."""
+    return ops.mask_apply_planar(specs, mask_real, mask_imag, mode)
 
 
 def magnitude_feature(spec, kind):

@@ -141,6 +141,50 @@ class _Mask(torch.autograd.Function):
         return gspec, gmask, None, None
 
 
+class _MaskPlanar(torch.autograd.Function):
+    """DCCRN layout: specs [rows,2F,T] planar, masks [rows,F,T] x 2 -> out [rows,2F,T] (one launch each way)."""
+
+    @staticmethod
+    def forward(ctx, specs, mre, mim, mode):
+        nv.require_cuda_f32(specs, mre, mim)
+        rows, nf2, nt = specs.shape
+        out = torch.empty_like(specs)
+        with nv.on_device(specs.device):
+            nv.check(nv.lib().se_mask_planar_fwd(specs.data_ptr(), mre.data_ptr(), mim.data_ptr(), out.data_ptr(), rows,
+                                                 nf2 // 2, nt, mode, nv.stream_ptr(specs.device)))
+        ctx.save_for_backward(specs, mre, mim)
+        ctx.mode = mode
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        specs, mre, mim = ctx.saved_tensors
+        rows, nf2, nt = specs.shape
+        g = g.contiguous()
+        gre, gim = torch.empty_like(mre), torch.empty_like(mim)
+        gspec = torch.empty_like(specs) if ctx.needs_input_grad[0] else None
+        with nv.on_device(specs.device):
+            nv.check(nv.lib().se_mask_planar_bwd(specs.data_ptr(), mre.data_ptr(), mim.data_ptr(), g.data_ptr(), gre.data_ptr(),
+                                                 gim.data_ptr(), _ptr(gspec), rows, nf2 // 2, nt, ctx.mode,
+                                                 nv.stream_ptr(specs.device)))
+        return gspec, gre, gim, None
+
+
+def mask_apply_planar(specs, mask_real, mask_imag, mode):
+    """specs [..., 2F, T] (Re bins then Im bins), masks [..., F, T]; returns a tensor shaped like specs."""
+    if mode not in ("E", "C", "R"):
+        raise ValueError(f"unknown DCCRN masking mode {mode!r}")
+    if specs.dim() < 2 or specs.shape[-2] % 2:
+        raise ValueError(f"expected specs [..., 2F, T], got {tuple(specs.shape)}")
+    want = tuple(specs.shape[:-2]) + (specs.shape[-2] // 2, specs.shape[-1])
+    if tuple(mask_real.shape) != want or tuple(mask_imag.shape) != want:
+        raise ValueError(f"mask shapes {tuple(mask_real.shape)}, {tuple(mask_imag.shape)} do not match specs {tuple(specs.shape)}")
+    lead = specs.shape[:-2]
+    s3 = _as_f32(specs).contiguous().reshape(-1, specs.shape[-2], specs.shape[-1])
+    m3 = [_as_f32(m).contiguous().reshape(-1, want[-2], want[-1]) for m in (mask_real, mask_imag)]
+    return _MaskPlanar.apply(s3, m3[0], m3[1], nv.MASK_MODES[mode]).reshape(*lead, specs.shape[-2], specs.shape[-1])
+
+
 def mask_apply(spec, mask, mode, pre_tanh=False):
     """spec [...,2], mask [...] ('real') or [...,2]; returns a tensor shaped like spec."""
     if mode not in nv.MASK_MODES:

@@ -121,6 +121,22 @@ def mask_bwd(spec, mask, gout, mode, pre_tanh, want_gspec=True):
     return gm, gs
 
 
+def mask_planar_fwd(specs, mre, mim, mode):
+    rows, nf2, nt = specs.shape
+    out = np.full(specs.shape, np.nan, np.float32)
+    check(lib().se_mask_planar_fwd(ptr(specs), ptr(mre), ptr(mim), ptr(out), i64(rows), i64(nf2 // 2), i64(nt), ci(mode), None))
+    return out
+
+
+def mask_planar_bwd(specs, mre, mim, gout, mode, want_gspec=True):
+    rows, nf2, nt = specs.shape
+    gre, gim = np.full(mre.shape, np.nan, np.float32), np.full(mim.shape, np.nan, np.float32)
+    gs = np.full(specs.shape, np.nan, np.float32) if want_gspec else None
+    check(lib().se_mask_planar_bwd(ptr(specs), ptr(mre), ptr(mim), ptr(gout), ptr(gre), ptr(gim), ptr(gs) if want_gspec else None,
+                                   i64(rows), i64(nf2 // 2), i64(nt), ci(mode), None))
+    return gre, gim, gs
+
+
 def mrstft_fwd(est, ref):
     rows, N = est.shape
     ws = np.zeros(lib().se_mrstft_workspace_bytes(rows, N) // 8 + 1, np.float64)

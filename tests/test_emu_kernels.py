@@ -150,6 +150,30 @@ def test_emu_mask_matches_dcunet_and_dccrn_golden():
         assert rel(np.concatenate([out[..., 0], out[..., 1]], 1), g["out_spec"]) < 1e-5
 
 
+@pytest.mark.parametrize("mode,code", [("E", 1), ("C", 2), ("R", 3)])
+def test_emu_planar_dccrn_mask(mode, code):
+    """DCCRN-layout mask kernels (se_mask_planar_fwd/bwd): the reference's golden vectors, and forward + all three
+    gradients against the interleaved kernels on a shape whose plane is odd (row bases lose 8-byte alignment)."""
+    g = golden(f"dccrn_mask_{mode}")
+    specs, mre, mim = (np.ascontiguousarray(g[k]) for k in ("specs", "mask_re", "mask_im"))
+    assert rel(E.mask_planar_fwd(specs, mre, mim, code), g["out_spec"]) < 1e-5
+    rng = np.random.default_rng(code)
+    nf, nt = 9, 7
+    specs = rng.standard_normal((3, 2 * nf, nt)).astype(np.float32)
+    specs[1, 0, 0] = specs[1, nf, 0] = 0.0                     # atan2(0,0) corner
+    mre, mim = (rng.standard_normal((3, nf, nt)).astype(np.float32) for _ in range(2))
+    go = rng.standard_normal(specs.shape).astype(np.float32)
+    inter = lambda a: np.ascontiguousarray(np.stack([a[:, :nf], a[:, nf:]], -1))
+    planar = lambda a: np.concatenate([a[..., 0], a[..., 1]], 1)
+    spec_i, mask_i = inter(specs), np.ascontiguousarray(np.stack([mre, mim], -1))
+    assert np.array_equal(E.mask_planar_fwd(specs, mre, mim, code), planar(E.mask_fwd(spec_i, mask_i, code, False)))
+    gm_i, gs_i = E.mask_bwd(spec_i, mask_i, inter(go), code, False)
+    gre, gim, gs = E.mask_planar_bwd(specs, mre, mim, go, code)
+    assert np.array_equal(gre, gm_i[..., 0]) and np.array_equal(gim, gm_i[..., 1]) and np.array_equal(gs, planar(gs_i))
+    gre2, gim2, none = E.mask_planar_bwd(specs, mre, mim, go, code, want_gspec=False)
+    assert none is None and np.array_equal(gre2, gre) and np.array_equal(gim2, gim)
+
+
 def test_emu_mrstft_loss_and_grad():
     rng = np.random.default_rng(1)
     N = 5000

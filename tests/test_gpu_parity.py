@@ -163,6 +163,35 @@ def test_mask_golden_from_reference_models(se):
         assert rel(out, torch.from_numpy(g["out_spec"])) < TOL_SPEC
 
 
+@pytest.mark.parametrize("mode", ["E", "C", "R"])
+def test_dccrn_planar_mask_matches_interleaved_and_autograd(se, oref, mode):
+    """apply_mask_dccrn (one planar kernel each way) against the interleaved kernels composed with stack / cat, and
+    against the oracle's autograd, at DCCRN's real shape [B,514,643]."""
+    from speech_enhancement_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(31)
+    specs = torch.randn(3, 514, 643, generator=g)
+    mre, mim = torch.randn(3, 257, 643, generator=g), torch.randn(3, 257, 643, generator=g)
+    go = torch.randn(3, 514, 643, generator=g)
+    a = [t.cuda().requires_grad_(True) for t in (specs, mre, mim)]
+    out = se.apply_mask_dccrn(a[0], a[1], a[2], mode)
+    ga = torch.autograd.grad(out, a, go.cuda())
+    b = [t.cuda().requires_grad_(True) for t in (specs, mre, mim)]
+    spec_i = torch.stack([b[0][:, :257], b[0][:, 257:]], -1)
+    o2 = ops.mask_apply(spec_i, torch.stack([b[1], b[2]], -1), mode, False)
+    out2 = torch.cat([o2[..., 0], o2[..., 1]], 1)
+    gb = torch.autograd.grad(out2, b, go.cuda())
+    assert rel(out, out2) < 1e-6              # same per-bin math; FMA contraction may differ between the two kernels
+    for x, y in zip(ga, gb):
+        assert rel(x, y) < 1e-6
+    c = [t.double().requires_grad_(True) for t in (specs, mre, mim)]
+    o3 = oref.mask_apply_ref(torch.stack([c[0][:, :257], c[0][:, 257:]], -1), torch.stack([c[1], c[2]], -1), mode, False)
+    out3 = torch.cat([o3[..., 0], o3[..., 1]], 1)
+    gc = torch.autograd.grad(out3, c, go.double())
+    assert rel(out, out3) < TOL_SPEC
+    for x, y in zip(ga, gc):
+        assert rel(x, y) < TOL_GRAD
+
+
 @pytest.mark.parametrize("shape", [(2, 1, 6000), (3, 2, 1, 16000)])
 def test_mrstft_loss_and_gradient(se, oref, shape):
     g = torch.Generator().manual_seed(1236)
