@@ -222,6 +222,17 @@ int se_conv_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe,
 int se_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t out_len,
                       int win_len, int win_inc, int fft_len, void* stream);
 
+/* ---- DCCRN's model tail + ConviSTFT in one launch each way (src/model/dccrn.py:203-224: mask, cat, self.istft):
+ * spec [rows,2F,T] is the UNMASKED spectrum, mask_re / mask_im [rows,F,T] (padded at DC by the model, dccrn.py:200-201),
+ * mode = SE_MASK_E / C / R.  fwd -> y [rows,out_len]; bwd: gy -> gradients wrt the two mask planes.  The masked
+ * spectrum and its gradient never touch memory. */
+int se_conv_mask_istft_fwd(const float* spec, const float* mask_re, const float* mask_im, float* y, int64_t rows,
+                           int64_t nframe, int64_t out_len, int win_len, int win_inc, int fft_len, int mode,
+                           void* stream);
+int se_conv_mask_istft_bwd(const float* gy, const float* spec, const float* mask_re, const float* mask_im,
+                           float* gmask_re, float* gmask_im, int64_t rows, int64_t nframe, int64_t out_len,
+                           int win_len, int win_inc, int fft_len, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

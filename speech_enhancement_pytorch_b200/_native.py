@@ -26,7 +26,7 @@ EXPORTS = (
     "se_spectral_loss_bwd", "se_sisnr_fwd", "se_sisnr_bwd", "se_psa_workspace_bytes", "se_psa_loss_fwd", "se_psa_loss_bwd", "se_enhance_fwd", "se_enhance_bwd",
     "se_mask_istft_fwd", "se_mask_istft_bwd", "se_overlap_add_fwd", "se_overlap_add_bwd",
     "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
-    "se_mask_planar_fwd", "se_mask_planar_bwd",
+    "se_mask_planar_fwd", "se_mask_planar_bwd", "se_conv_mask_istft_fwd", "se_conv_mask_istft_bwd",
     "se_p2p_create", "se_p2p_open", "se_p2p_close", "se_p2p_destroy", "se_mrstft_exchange_value",
 )
 
@@ -138,6 +138,8 @@ def lib():
             L.se_conv_istft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]
             L.se_mask_planar_fwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _PTR]
             L.se_mask_planar_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _PTR]
+            L.se_conv_mask_istft_fwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _PTR]
+            L.se_conv_mask_istft_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _PTR]
             L.se_p2p_create.argtypes = [_c.POINTER(_PTR), _c.c_char_p]
             L.se_p2p_open.argtypes = [_c.c_char_p, _c.POINTER(_PTR)]
             L.se_p2p_close.argtypes = [_PTR]

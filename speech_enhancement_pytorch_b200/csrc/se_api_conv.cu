@@ -70,3 +70,44 @@ extern "C" int se_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, in
     cudaError_t e = launch(k_conv_istft_adj<G>, (unsigned)(rows * a.nchunks), G::NT, ConvGeo<G>::ADJ, (cudaStream_t)stream, a);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_istft_bwd launch");
 }
+
+// ---- DCCRN model tail + ConviSTFT in one launch each way (src/model/dccrn.py:203-224): the masked spectrum and its
+// gradient are never written
+#define SE_DISPATCH_CONV_MODE(mode, CALL)                                                \
+    do {                                                                                 \
+        if (mode == 1) { constexpr int MODE = 1; CALL; }                                 \
+        else if (mode == 2) { constexpr int MODE = 2; CALL; }                            \
+        else { constexpr int MODE = 3; CALL; }                                           \
+    } while (0)
+
+extern "C" int se_conv_mask_istft_fwd(const float* spec, const float* mask_re, const float* mask_im, float* y, int64_t rows,
+                                      int64_t nframe, int64_t out_len, int win_len, int win_inc, int fft_len, int mode, void* stream) {
+    if (!spec || !mask_re || !mask_im || !y) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (mode < 1 || mode > 3) return fail(SE_ERR_UNSUPPORTED, "DCCRN mask mode must be E/C/R");
+    ConvArgs a{};
+    if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len)) return rc;
+    a.in = spec; a.mre = mask_re; a.mim = mask_im; a.out = y;
+    a.b_lo = a.pad / win_inc; a.b_hi = (int)((a.pad + out_len + win_inc - 1) / win_inc);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, 4, 2, 16);
+    using G = Geo<512, 100, 256>;
+    cudaError_t e;
+    SE_DISPATCH_CONV_MODE(mode, (e = launch(k_conv_istft<G, MODE>, (unsigned)(rows * a.nchunks), G::NT, ConvGeo<G>::SYNTH,
+                                            (cudaStream_t)stream, a)));
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_mask_istft_fwd launch");
+}
+
+extern "C" int se_conv_mask_istft_bwd(const float* gy, const float* spec, const float* mask_re, const float* mask_im,
+                                      float* gmask_re, float* gmask_im, int64_t rows, int64_t nframe, int64_t out_len, int win_len,
+                                      int win_inc, int fft_len, int mode, void* stream) {
+    if (!gy || !spec || !mask_re || !mask_im || !gmask_re || !gmask_im) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (mode < 1 || mode > 3) return fail(SE_ERR_UNSUPPORTED, "DCCRN mask mode must be E/C/R");
+    ConvArgs a{};
+    if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len)) return rc;
+    a.in = gy; a.spec = spec; a.mre = mask_re; a.mim = mask_im; a.gre = gmask_re; a.gim = gmask_im;
+    plan_analysis(rows, nframe, a.gpc, a.nchunks, 16);
+    using G = Geo<512, 100, 256>;
+    cudaError_t e;
+    SE_DISPATCH_CONV_MODE(mode, (e = launch(k_conv_istft_adj<G, MODE>, (unsigned)(rows * a.nchunks), G::NT, ConvGeo<G>::ADJ,
+                                            (cudaStream_t)stream, a)));
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_mask_istft_bwd launch");
+}

@@ -21,6 +21,12 @@ struct ConvArgs {
     int b_lo, b_hi, nchunks;             // synthesis chunking
     int gpc;                             // adjoint (analysis-style) chunking
     float inv_even, inv_odd;             // 1 / (n/2 + #even), 1 / (n/2 + #odd)
+    // fused DCCRN tail (MODE >= 1): `in` / `spec` is the UNMASKED spectrum, the masks are two planes [rows,F,T]
+    const float* spec;                   // bwd: unmasked spectrum (fwd reads it through `in`)
+    const float* mre;
+    const float* mim;
+    float* gre;                          // bwd: gradient wrt the mask planes (replaces `out`)
+    float* gim;
 };
 
 template <class G> struct ConvGeo {
@@ -47,26 +53,41 @@ __device__ __forceinline__ float2 frame_parity_sums(float2 part, float2* red, in
     return tot;
 }
 
-template <class G>
-__device__ __forceinline__ void load_task_planar(const float* __restrict__ row, int T, int t, int p,
+// MODE < 0: plain spectrum; MODE 1/2/3: the DCCRN mask tail (dccrn.py:203-221) applied to the bins as they are loaded
+template <class G, int MODE>
+__device__ __forceinline__ void load_task_planar(const float* __restrict__ row, const float* __restrict__ mre,
+                                                 const float* __restrict__ mim, int T, int t, int p,
                                                  float2* ya, float2* yb, float2& nyq) {
     const bool ok = (t >= 0 && t < T);
+    const int tc = ok ? t : 0;                                   // clamped: loads stay in bounds, result zeroed
     const int qa = task_qa<G>(p), qb = task_qb<G>(p);
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
-        const int ka = qa + G::S * k4, kb = qb + G::S * k4;
-        ya[k4] = ok ? make_float2(__ldg(row + (size_t)ka * T + t), __ldg(row + (size_t)(G::F + ka) * T + t)) : make_float2(0.f, 0.f);
-        yb[k4] = ok ? make_float2(__ldg(row + (size_t)kb * T + t), __ldg(row + (size_t)(G::F + kb) * T + t)) : make_float2(0.f, 0.f);
+        const size_t ia = (size_t)(qa + G::S * k4) * T + tc, ib = (size_t)(qb + G::S * k4) * T + tc;
+        const size_t im = (size_t)G::F * T;
+        ya[k4] = make_float2(__ldg(row + ia), __ldg(row + im + ia));
+        yb[k4] = make_float2(__ldg(row + ib), __ldg(row + im + ib));
+        if (MODE >= 0) {
+            ya[k4] = MaskMath::apply<(MODE >= 0 ? MODE : 2), false>(ya[k4], make_float2(__ldg(mre + ia), __ldg(mim + ia)));
+            yb[k4] = MaskMath::apply<(MODE >= 0 ? MODE : 2), false>(yb[k4], make_float2(__ldg(mre + ib), __ldg(mim + ib)));
+        }
+        if (!ok) ya[k4] = yb[k4] = make_float2(0.f, 0.f);
     }
     nyq = make_float2(0.f, 0.f);
     if (p == 0) {
-        if (ok) nyq = make_float2(__ldg(row + (size_t)G::M * T + t), 0.f);
+        if (ok) {
+            const size_t in = (size_t)G::M * T + tc;
+            if (MODE >= 0) nyq = MaskMath::apply<(MODE >= 0 ? MODE : 2), false>(
+                               make_float2(__ldg(row + in), __ldg(row + (size_t)G::F * T + in)), make_float2(__ldg(mre + in), __ldg(mim + in)));
+            else nyq = make_float2(__ldg(row + in), 0.f);
+            nyq.y = 0.f;
+        }
         ya[0].x *= 2.f;          // H = Y / c_k with the 1/2 folded into the window: edges weigh 2
         nyq.x *= 2.f;
     }
 }
 
-template <class G>
+template <class G, int MODE = -1>
 __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a) {
     using C = ConvGeo<G>;
     SE_SMEM_DECL;
@@ -96,7 +117,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
         for (int i = 0; i < G::TC; ++i) {
             const int p = unit + i * G::NU;
             float2 ya[8], yb[8], nyq;
-            load_task_planar<G>(spec, a.nframe, t, p, ya, yb, nyq);
+            const size_t moff = (size_t)row * G::F * a.nframe;
+            load_task_planar<G, MODE>(spec, MODE >= 0 ? a.mre + moff : nullptr, MODE >= 0 ? a.mim + moff : nullptr, a.nframe, t, p, ya, yb, nyq);
             synthesis_task<G>(zb, tb, p, fr, ya, yb, nyq);
         }
         __syncthreads();
@@ -161,8 +183,9 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft(const ConvArgs a)
     }
 }
 
-// adjoint of k_conv_istft: gy [rows,out_len] -> gspec [rows,2F,T] planar
-template <class G>
+// adjoint of k_conv_istft: gy [rows,out_len] -> gspec [rows,2F,T] planar; MODE >= 1: continue through the mask tail
+// to the gradient wrt the two mask planes (gspec is never written)
+template <class G, int MODE = -1>
 __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArgs a) {
     using C = ConvGeo<G>;
     SE_SMEM_DECL;
@@ -240,7 +263,27 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_conv_istft_adj(const ConvArg
             const int p = unit + i * G::NU;
             float2 xa[8], xb[8], nyq;
             analysis_task<G>(zb, tb, p, fr, xa, xb, nyq);
-            store_task_planar<G>(out_row, a.nframe, t, p, xa, xb, nyq);
+            if (MODE < 0) {
+                store_task_planar<G>(out_row, a.nframe, t, p, xa, xb, nyq);
+            } else if (t < a.nframe) {
+                constexpr int MM = MODE >= 0 ? MODE : 2;
+                const size_t moff = (size_t)row * G::F * a.nframe, im = (size_t)G::F * a.nframe;
+                const float* x_row = a.spec + 2 * moff;
+                const int qa = task_qa<G>(p), qb = task_qb<G>(p);
+#pragma unroll
+                for (int k = 0; k < 17; ++k) {
+                    if (k == 16 && p != 0) continue;
+                    const int bin = k < 8 ? qa + G::S * k : (k < 16 ? qb + G::S * (k - 8) : G::M);
+                    float2 gy = k < 8 ? xa[k] : (k < 16 ? xb[k - 8] : nyq);
+                    if (bin == 0 || bin == G::M) gy.y = 0.f;              // imaginary grads at DC / Nyquist are exactly 0
+                    const size_t idx = (size_t)bin * a.nframe + t;
+                    float2 gm, gx;
+                    MaskMath::grad<MM, false>(make_float2(__ldg(x_row + idx), __ldg(x_row + im + idx)),
+                                              make_float2(__ldg(a.mre + moff + idx), __ldg(a.mim + moff + idx)), gy, gm, gx);
+                    a.gre[moff + idx] = gm.x;
+                    a.gim[moff + idx] = gm.y;
+                }
+            }
         }
         __syncthreads();
     }

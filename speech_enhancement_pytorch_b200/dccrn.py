@@ -72,3 +72,23 @@ class ConviSTFT(torch.nn.Module):
         else:
             out_len = natural
         return ops.conv_istft_rows(inputs, out_len, self.win_len, self.stride, self.fft_len).unsqueeze(1)
+
+    def _out_len(self, nt):
+        pad = self.win_len - self.stride
+        natural = self.stride * (nt - 1) + self.win_len - 2 * pad
+        return min(int(self.length), natural + pad) if self.length else natural
+
+    def forward_masked(self, specs, mask_real, mask_imag, mode="E"):
+        """`self(apply_mask_dccrn(specs, mask_real, mask_imag, mode))` -- DCCRN's tail, src/model/dccrn.py:203-224 --
+        in one launch each way: the masked spectrum (and its gradient) is never written.  specs [B,2F,T] is data
+        (ConvSTFT of the mixture); when it requires grad the two-stage composition runs instead."""
+        from .masking import apply_mask_dccrn
+        if mode not in ("E", "C", "R"):
+            raise ValueError(f"unknown DCCRN masking mode {mode!r}")
+        if specs.requires_grad:
+            return self(apply_mask_dccrn(specs, mask_real, mask_imag, mode))
+        want = (specs.shape[0], specs.shape[1] // 2, specs.shape[2])
+        if specs.dim() != 3 or tuple(mask_real.shape) != want or tuple(mask_imag.shape) != want:
+            raise ValueError(f"mask shapes {tuple(mask_real.shape)}, {tuple(mask_imag.shape)} do not match specs {tuple(specs.shape)}")
+        return ops.conv_mask_istft_rows(specs, mask_real, mask_imag, self._out_len(specs.shape[-1]), self.win_len, self.stride,
+                                        self.fft_len, mode).unsqueeze(1)

@@ -525,5 +525,39 @@ class _ConvISTFT(torch.autograd.Function):
         return g, None, None, None, None
 
 
+class _ConvMaskISTFT(torch.autograd.Function):
+    """ConviSTFT(apply_mask_dccrn(specs, mask_re, mask_im)) in one launch each way; gradient to the two mask planes."""
+
+    @staticmethod
+    def forward(ctx, spec, mre, mim, out_len, win_len, win_inc, fft_len, mode):
+        nv.require_cuda_f32(spec, mre, mim)
+        rows, _, nt = spec.shape
+        y = torch.empty((rows, out_len), dtype=torch.float32, device=spec.device)
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_conv_mask_istft_fwd(spec.data_ptr(), mre.data_ptr(), mim.data_ptr(), y.data_ptr(), rows, nt,
+                                                     out_len, win_len, win_inc, fft_len, mode, nv.stream_ptr(spec.device)))
+        ctx.save_for_backward(spec, mre, mim)
+        ctx.cfg = (out_len, win_len, win_inc, fft_len, mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        spec, mre, mim = ctx.saved_tensors
+        out_len, win_len, win_inc, fft_len, mode = ctx.cfg
+        rows, _, nt = spec.shape
+        gy = gy.contiguous()
+        gre, gim = torch.empty_like(mre), torch.empty_like(mim)
+        with nv.on_device(spec.device):
+            nv.check(nv.lib().se_conv_mask_istft_bwd(gy.data_ptr(), spec.data_ptr(), mre.data_ptr(), mim.data_ptr(),
+                                                     gre.data_ptr(), gim.data_ptr(), rows, nt, out_len, win_len, win_inc,
+                                                     fft_len, mode, nv.stream_ptr(spec.device)))
+        return None, gre, gim, None, None, None, None, None
+
+
+def conv_mask_istft_rows(spec, mask_real, mask_imag, out_len, win_len, win_inc, fft_len, mode):
+    return _ConvMaskISTFT.apply(_as_f32(spec).contiguous(), _as_f32(mask_real).contiguous(), _as_f32(mask_imag).contiguous(),
+                                int(out_len), win_len, win_inc, fft_len, nv.MASK_MODES[mode])
+
+
 def conv_istft_rows(spec, out_len, win_len, win_inc, fft_len):
     return _ConvISTFT.apply(_as_f32(spec).contiguous(), int(out_len), win_len, win_inc, fft_len)

@@ -248,3 +248,20 @@ def spectral_loss(enh, target, n, hop, win, kind, gout=1.0):
     check(lib().se_spectral_loss_bwd(ptr(enh), ptr(target), ptr(go), i64(rows), i64(rows), i64(N), ci(n), ci(hop), ci(win),
                                      f32(1.0 / win), ci(kind), ptr(g), None))
     return float(total[0]) / (enh.size), g
+
+
+def conv_mask_istft_fwd(spec, mre, mim, out_len, win_len, win_inc, fft_len, mode):
+    rows, _, T = spec.shape
+    out = np.full((rows, out_len), np.nan, np.float32)
+    check(lib().se_conv_mask_istft_fwd(ptr(spec), ptr(mre), ptr(mim), ptr(out), i64(rows), i64(T), i64(out_len), ci(win_len),
+                                       ci(win_inc), ci(fft_len), ci(mode), None))
+    return out
+
+
+def conv_mask_istft_bwd(gy, spec, mre, mim, win_len, win_inc, fft_len, mode):
+    rows, out_len = gy.shape
+    T = spec.shape[-1]
+    gre, gim = np.full(mre.shape, np.nan, np.float32), np.full(mim.shape, np.nan, np.float32)
+    check(lib().se_conv_mask_istft_bwd(ptr(gy), ptr(spec), ptr(mre), ptr(mim), ptr(gre), ptr(gim), i64(rows), i64(T), i64(out_len),
+                                       ci(win_len), ci(win_inc), ci(fft_len), ci(mode), None))
+    return gre, gim

@@ -174,6 +174,27 @@ def test_emu_planar_dccrn_mask(mode, code):
     assert none is None and np.array_equal(gre2, gre) and np.array_equal(gim2, gim)
 
 
+@pytest.mark.parametrize("mode,code", [("E", 1), ("C", 2), ("R", 3)])
+def test_emu_fused_dccrn_tail(mode, code):
+    """se_conv_mask_istft_fwd/bwd = ConviSTFT(mask tail) and its gradient wrt the two mask planes, against the two-stage
+    emulated kernels (planar mask, then ConviSTFT / its adjoint, then the mask adjoint)."""
+    rng = np.random.default_rng(40 + code)
+    T, out_len = 37, 3000
+    spec = rng.standard_normal((2, 514, T)).astype(np.float32)
+    mre, mim = (rng.standard_normal((2, 257, T)).astype(np.float32) for _ in range(2))
+    mre[:, 0] = mim[:, 0] = 0.0                                  # the model pads the masks at DC (dccrn.py:200-201)
+    y = E.conv_mask_istft_fwd(spec, mre, mim, out_len, 400, 100, 512, code)
+    masked = E.mask_planar_fwd(spec, mre, mim, code)
+    want = E.conv_istft_fwd(masked, out_len, 400, 100, 512)
+    assert not np.isnan(y).any() and rel(y, want) < 1e-6
+    gy = rng.standard_normal(y.shape).astype(np.float32)
+    gre, gim = E.conv_mask_istft_bwd(gy, spec, mre, mim, 400, 100, 512, code)
+    gmasked = E.conv_istft_bwd(gy, T, 400, 100, 512)
+    wre, wim, _ = E.mask_planar_bwd(spec, mre, mim, gmasked, code)
+    assert not (np.isnan(gre).any() or np.isnan(gim).any())
+    assert rel(gre, wre) < 1e-6 and rel(gim, wim) < 1e-6
+
+
 def test_emu_mrstft_loss_and_grad():
     rng = np.random.default_rng(1)
     N = 5000

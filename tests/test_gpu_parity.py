@@ -192,6 +192,46 @@ def test_dccrn_planar_mask_matches_interleaved_and_autograd(se, oref, mode):
         assert rel(x, y) < TOL_GRAD
 
 
+@pytest.mark.parametrize("mode", ["E", "C", "R"])
+def test_dccrn_fused_tail_matches_two_stage_and_oracle(se, oref, mode):
+    """ConviSTFT.forward_masked (mask tail + ConviSTFT in one launch each way) against istft(apply_mask_dccrn(...)) and,
+    through autograd, against the oracle's float64 composition; DCCRN's real shape."""
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(3, 1, 64000, generator=g)
+    mre, mim = torch.randn(3, 257, 643, generator=g), torch.randn(3, 257, 643, generator=g)
+    mre[:, 0] = 0.0
+    mim[:, 0] = 0.0
+    gy = torch.randn(3, 1, 64000, generator=g)
+    st, ist = se.ConvSTFT(400, 100, 512, "hann", "complex"), se.ConviSTFT(400, 100, 512, 64000, "hann", "complex")
+    specs = st(x.cuda())
+    a = [t.cuda().requires_grad_(True) for t in (mre, mim)]
+    y = ist.forward_masked(specs, a[0], a[1], mode)
+    ga = torch.autograd.grad(y, a, gy.cuda())
+    b = [t.cuda().requires_grad_(True) for t in (mre, mim)]
+    y2 = ist(se.apply_mask_dccrn(specs, b[0], b[1], mode))
+    gb = torch.autograd.grad(y2, b, gy.cuda())
+    assert y.shape == y2.shape == (3, 1, 64000)
+    assert rel(y, y2) < 1e-6
+    for u, v in zip(ga, gb):
+        assert rel(u, v) < 1e-5
+    # oracle: the reference's mask expressions + conv_transpose1d ConviSTFT in float64
+    c = [t.double().requires_grad_(True) for t in (mre, mim)]
+    sp = specs.detach().cpu().double()
+    o = oref.mask_apply_ref(torch.stack([sp[:, :257], sp[:, 257:]], -1), torch.stack([c[0], c[1]], -1), mode, False)
+    y3 = oref.conv_istft_ref(torch.cat([o[..., 0], o[..., 1]], 1), 400, 100, 512, length=64000)
+    gc = torch.autograd.grad(y3, c, gy.double().reshape(y3.shape))
+    assert rel(y, y3.reshape(y.shape)) < TOL_SPEC
+    # DC row excluded: the masks are zero-padded there (dccrn.py:200-201; F.pad drops that gradient) and the
+    # reference's polar expression has a NaN derivative at an exactly-zero mask
+    for u, v in zip(ga, gc):
+        assert rel(u[:, 1:], v[:, 1:]) < TOL_GRAD
+    # a spectrum that requires grad takes the two-stage path
+    s2 = specs.detach().clone().requires_grad_(True)
+    y4 = ist.forward_masked(s2, a[0], a[1], mode)
+    (gs,) = torch.autograd.grad(y4, s2, gy.cuda())
+    assert gs.shape == specs.shape and rel(y4, y2) < 1e-6
+
+
 @pytest.mark.parametrize("shape", [(2, 1, 6000), (3, 2, 1, 16000)])
 def test_mrstft_loss_and_gradient(se, oref, shape):
     g = torch.Generator().manual_seed(1236)

@@ -59,6 +59,9 @@ def main():
     with torch.no_grad():
         us = timed(lambda s: ist(se.apply_mask_dccrn(st(s[0]), s[1], s[2], "E")), sets)
     out["cfg4_dccrn_transforms_16x4s"] = {"us": round(us, 1), "audio_s_per_s": round(64 / us * 1e6)}
+    with torch.no_grad():
+        us = timed(lambda s: ist.forward_masked(st(s[0]), s[1], s[2], "E"), sets)
+    out["cfg4_dccrn_fused_tail_16x4s"] = {"us": round(us, 1), "audio_s_per_s": round(64 / us * 1e6)}
     # cfg 5: 44.1 kHz stereo 30 s clips, 8 clips, n_fft 2048 and 1024, complex mask, fused and unfused
     for n in (2048, 1024):
         c = cfg(n, n // 4)
