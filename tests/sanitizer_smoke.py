@@ -44,6 +44,26 @@ def main():
     st, ist = se.ConvSTFT(400, 100, 512, "hann", "complex"), se.ConviSTFT(400, 100, 512, 3000, "hann", "complex")
     s = st(torch.randn(2, 1, 3000, device=dev)).requires_grad_(True)
     ist(s).sum().backward()
+    # DCCRN tail on its planar layout, and fused into ConviSTFT
+    for mode in ("E", "C", "R"):
+        mre, mim = (torch.randn(2, 257, s.shape[-1], device=dev, requires_grad=True) for _ in range(2))
+        se.apply_mask_dccrn(s, mre, mim, mode).square().sum().backward()
+        ist.forward_masked(s.detach(), mre, mim, mode).square().sum().backward()
+    se.loss_phase_sensitive_spectral_approximation(spec.detach().clone().requires_grad_(True), spec.detach() * 0.5,
+                                                   spec.detach() * 1.5).backward()
+    # the peer-memory exchange kernel with a world of one (same code path: post, flag, poll, rank-ordered sum, value)
+    import ctypes
+    from speech_enhancement_pytorch_b200 import _native as nv
+    L = nv.lib()
+    local, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    nv.check(L.se_p2p_create(ctypes.byref(local), handle))
+    ptrs = (ctypes.c_void_p * 1)(local.value)
+    sums = torch.rand(9, dtype=torch.float64, device=dev) + 1.0
+    loss = torch.empty((), device=dev)
+    for _ in range(3):
+        nv.check(L.se_mrstft_exchange_value(sums.data_ptr(), ptrs, 1, 0, 3, 7000, loss.data_ptr(), nv.stream_ptr(torch.device(dev, 0))))
+    torch.cuda.synchronize()
+    nv.check(L.se_p2p_destroy(local))
     cfg = types.SimpleNamespace(dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
                                 model=types.SimpleNamespace(name="dnn", segment=0.256, n_fft=512, hop_length=128,
                                                             win_length=512, center=True))

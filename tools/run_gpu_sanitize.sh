@@ -2,6 +2,9 @@
 set -u
 mkdir -p gpurun_out
 for tool in memcheck racecheck initcheck; do
-  timeout 1500 compute-sanitizer --tool $tool --launch-timeout 0 python tests/sanitizer_smoke.py > gpurun_out/sanitizer_$tool.log 2>&1
+  timeout 700 compute-sanitizer --tool $tool --launch-timeout 0 python tests/sanitizer_smoke.py > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer smoke done" gpurun_out/sanitizer_$tool.log | tail -3
 done
+# the opt-in saved-spectrum loss backward
+SE_MRSTFT_SAVE_SPECTRUM=1 timeout 600 compute-sanitizer --tool memcheck --launch-timeout 0 python tests/sanitizer_smoke.py > gpurun_out/sanitizer_memcheck_saved.log 2>&1
+echo "memcheck (saved spectrum) rc=$?"; grep -E "ERROR SUMMARY|sanitizer smoke done" gpurun_out/sanitizer_memcheck_saved.log | tail -2
