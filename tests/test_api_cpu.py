@@ -74,3 +74,39 @@ def test_fused_tail_and_tasnet_entry_points_validate_without_a_gpu():
         se.SI_SDR(torch.randn(2, 100), torch.randn(2, 100))
     with pytest.raises(ValueError):
         se.SI_SDR(torch.randn(2, 100), torch.randn(2, 99))
+
+
+def test_dccrn_tail_entry_points_validate_without_a_gpu():
+    specs, mre, mim = torch.randn(2, 514, 9), torch.randn(2, 257, 9), torch.randn(2, 257, 9)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.apply_mask_dccrn(specs, mre, mim, "E")
+    with pytest.raises(ValueError):
+        se.apply_mask_dccrn(specs, mre, mim, "real")                       # DCCRN has E / C / R only (dccrn.py:203-221)
+    with pytest.raises(ValueError):
+        se.apply_mask_dccrn(specs, mre[:, 1:], mim[:, 1:], "E")            # masks must be padded at DC (dccrn.py:200-201)
+    with pytest.raises(ValueError):
+        se.apply_mask_dccrn(torch.randn(2, 513, 9), mre, mim, "C")
+    ist = se.ConviSTFT(400, 100, 512, 600, "hann", "complex")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ist.forward_masked(specs, mre, mim, "E")
+    with pytest.raises(ValueError):
+        ist.forward_masked(specs, mre, mim, "Z")
+    with pytest.raises(ValueError):
+        ist.forward_masked(specs, mre[:, 1:], mim, "E")
+    assert ist._out_len(9) == 600 and se.ConviSTFT(400, 100, 512, None, "hann", "complex")._out_len(9) == 600
+
+
+def test_peer_exchange_binding_validates_without_a_gpu():
+    import ctypes
+    from speech_enhancement_pytorch_b200 import _native as nv
+    L = nv.lib()
+    buf = (ctypes.c_double * 9)()
+    ptrs = (ctypes.c_void_p * 2)(ctypes.addressof(buf), None)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.se_mrstft_exchange_value(None, ptrs, 2, 0, 4, 4096, None, None) == -1
+    assert L.se_mrstft_exchange_value(p, ptrs, 17, 0, 4, 4096, None, None) == -1       # at most 16 ranks
+    assert L.se_mrstft_exchange_value(p, ptrs, 2, 2, 4, 4096, None, None) == -1        # rank out of range
+    assert L.se_mrstft_exchange_value(p, ptrs, 2, 0, 4, 4096, None, None) == -1        # a peer buffer is missing
+    assert b"exchange buffer" in L.se_last_error()
+    assert L.se_mask_planar_fwd(p, p, p, p, 1, 4, 4, 0, None) == -2                     # REAL is not a DCCRN mode
+    assert L.se_conv_mask_istft_fwd(p, p, p, p, 1, 9, 600, 400, 100, 512, 7, None) == -2
