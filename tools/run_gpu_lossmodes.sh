@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B visit for the MR-STFT loss backward: saved-spectrum (default) vs recompute, launch order, cache hints
+# A/B visit for the MR-STFT loss backward: recompute (default) vs the opt-in saved-spectrum mode.
+# (The launch-order / cache-hint / geometry variants recorded in profiles/r01_notes.md (d) were measured with
+# temporary switches that have since been folded into the saved-spectrum path or removed.)
 set -u
 mkdir -p gpurun_out
 summ() { python - "$1" <<'PY'
@@ -14,13 +16,7 @@ run() { # name, env...
   env "$@" timeout 300 python bench.py --steps 40 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err || tail -3 gpurun_out/bench_$name.err
   summ gpurun_out/bench_$name.json
 }
-run recompute SE_MRSTFT_RECOMPUTE=1
-run saved X=1
-run saved_asc SE_MRSTFT_BWD_ASCENDING=1
-run saved_asc_h1 SE_MRSTFT_BWD_ASCENDING=1 SE_MRSTFT_HINTS=1
-run saved_asc_h2 SE_MRSTFT_BWD_ASCENDING=1 SE_MRSTFT_HINTS=2
-run saved_asc_h3 SE_MRSTFT_BWD_ASCENDING=1 SE_MRSTFT_HINTS=3
-run saved_asc_h4 SE_MRSTFT_BWD_ASCENDING=1 SE_MRSTFT_HINTS=4
-run saved_asc_h7 SE_MRSTFT_BWD_ASCENDING=1 SE_MRSTFT_HINTS=7
-run saved_h7 SE_MRSTFT_HINTS=7
-run recompute2 SE_MRSTFT_RECOMPUTE=1
+run recompute X=1
+run saved SE_MRSTFT_SAVE_SPECTRUM=1
+run recompute2 X=1
+run saved2 SE_MRSTFT_SAVE_SPECTRUM=1
