@@ -623,7 +623,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
                     } else if (t < a.nframe && !(k == 16 && p != 0)) {
                         const float ca = fmaxf(pw, SE_MRSTFT_CLAMP);
                         const float cb = fmaxf(pb[i][k], SE_MRSTFT_CLAMP);
-                        const float d = cb * se_rsqrt(cb) - ca * se_rsqrt(ca);
+                        // rounded products: identical spectra must give d == 0 exactly (loss(x, x) = 0, zero gradient)
+                        const float d = se_mul_rn(cb, se_rsqrt(cb)) - se_mul_rn(ca, se_rsqrt(ca));
                         s_d2 += d * d;
                         s_b2 += cb;
                         // |log b - log a| = ln2/2 |log2 cb - log2 ca|  (both clamped: normal range)

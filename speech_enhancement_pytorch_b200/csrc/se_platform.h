@@ -71,6 +71,16 @@ __device__ __forceinline__ float se_log2(float x) {
 #endif
 }
 
+// A product that must stay a rounded product: without this the compiler contracts `x*y - u*v` into an FMA whose
+// inner product is unrounded, so the difference of two bit-identical products comes out as their rounding error, not 0.
+__device__ __forceinline__ float se_mul_rn(float a, float b) {
+#ifdef SE_EMULATE
+    return a * b;
+#else
+    return __fmul_rn(a, b);
+#endif
+}
+
 // Evict-first store for scratch that is written once and read once, much later (the loss workspace): keeps it from
 // displacing the step's reusable lines in L2.
 template <class T>

@@ -299,6 +299,37 @@ def test_mrstft_loss_modes_agree(se, tmp_path, env):
     assert rel(torch.from_numpy(got["grad"]), grad) < 2e-5
 
 
+
+def test_mrstft_silent_and_identical_inputs(se, oref):
+    """log / clamp corners (SURVEY 8c fixtures): all-zero signals sit on the 1e-7 clamp, identical signals give a zero
+    numerator in the spectral-convergence term -- loss 0, gradient exactly 0, nothing non-finite; one silent row inside a
+    normal batch matches the oracle."""
+    z = torch.zeros(2, 1, 6000, device="cuda")
+    e = z.clone().requires_grad_(True)
+    loss = se.loss_mrstft(e, z)
+    (g,) = torch.autograd.grad(loss, e)
+    assert float(loss) == 0.0 and torch.count_nonzero(g) == 0
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 6000, generator=gen)
+    e = x.cuda().requires_grad_(True)
+    loss = se.loss_mrstft(e, x.cuda())
+    (g,) = torch.autograd.grad(loss, e)
+    assert float(loss) == 0.0 and torch.isfinite(g).all() and float(g.abs().max()) == 0.0
+    ref = torch.randn(3, 1, 6000, generator=gen)
+    est = ref + 0.1 * torch.randn(3, 1, 6000, generator=gen)
+    ref[1] = 0.0
+    est[1] = 0.0
+    e = est.cuda().requires_grad_(True)
+    loss = se.loss_mrstft(e, ref.cuda())
+    (g,) = torch.autograd.grad(loss, e)
+    er = est.clone().double().requires_grad_(True)
+    lr = oref.mrstft_loss_ref(er, ref.double())
+    (gr,) = torch.autograd.grad(lr, er)
+    assert torch.isfinite(g).all() and abs(float(loss) - float(lr)) < TOL_GRAD * float(lr)
+    assert float(g[1].abs().max()) == 0.0 and float(gr[1].abs().max()) == 0.0
+    assert rel(g, gr) < 2 * TOL_GRAD
+
+
 def test_mrstft_full_size_survey_value(se):
     """seed 1236, est = ref + 0.1 N(0,1), 128x1x64000 -> loss 0.168027."""
     g = torch.Generator().manual_seed(1236)
