@@ -174,6 +174,24 @@ def test_emu_planar_dccrn_mask(mode, code):
     assert none is None and np.array_equal(gre2, gre) and np.array_equal(gim2, gim)
 
 
+@pytest.mark.parametrize("groups", ["2", "3"])
+def test_emu_fused_dccrn_tail_multi_group_and_natural_length(groups, monkeypatch):
+    """The fused DCCRN tail with forced multi-group chunks (ring carry across groups) and with `length=None`
+    (natural length, both pads dropped), against the two-stage kernels planned the default way."""
+    rng = np.random.default_rng(7)
+    T = 61
+    natural = 100 * (T - 1) + 400 - 2 * 300
+    spec = rng.standard_normal((1, 514, T)).astype(np.float32)
+    mre, mim = (rng.standard_normal((1, 257, T)).astype(np.float32) for _ in range(2))
+    want = E.conv_istft_fwd(E.mask_planar_fwd(spec, mre, mim, 1), natural, 400, 100, 512)
+    gy = rng.standard_normal(want.shape).astype(np.float32)
+    wre, wim, _ = E.mask_planar_bwd(spec, mre, mim, E.conv_istft_bwd(gy, T, 400, 100, 512), 1)
+    monkeypatch.setenv("SE_FORCE_GROUPS", groups)
+    y = E.conv_mask_istft_fwd(spec, mre, mim, natural, 400, 100, 512, 1)
+    gre, gim = E.conv_mask_istft_bwd(gy, spec, mre, mim, 400, 100, 512, 1)
+    assert rel(y, want) < 1e-6 and rel(gre, wre) < 1e-6 and rel(gim, wim) < 1e-6
+
+
 @pytest.mark.parametrize("mode,code", [("E", 1), ("C", 2), ("R", 3)])
 def test_emu_fused_dccrn_tail(mode, code):
     """se_conv_mask_istft_fwd/bwd = ConviSTFT(mask tail) and its gradient wrt the two mask planes, against the two-stage
