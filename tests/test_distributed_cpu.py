@@ -55,3 +55,34 @@ def test_two_rank_loss_equals_global_loss():
     want = float(oref.mrstft_loss_ref(est, ref))
     assert abs(out[0] - out[1]) < 1e-12
     assert abs(out[0] - want) / want < 1e-5
+
+
+def _exchange_worker(rank, world, port, disabled, out):
+    import warnings
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), SE_P2P_EXCHANGE="0" if disabled else "1")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    with warnings.catch_warnings(record=True) as seen:
+        warnings.simplefilter("always")
+        px = sed.peer_exchange(dist.group.WORLD, torch.device("cuda", 0))
+        again = sed.peer_exchange(dist.group.WORLD, torch.device("cuda", 0))      # cached decision, no second gather
+    out[rank] = (px is None, again is None, [str(w.message) for w in seen])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("disabled", [False, True])
+def test_peer_exchange_falls_back_jointly_without_peer_memory(disabled):
+    """No GPU here, so no rank can create its exchange buffer: every rank must still take part in the two gathers,
+    agree on `None` (the caller then uses the NCCL / gloo all-reduce) and say why -- no hang, no exception.  With
+    SE_P2P_EXCHANGE=0 the buffers are not even attempted."""
+    if torch.cuda.is_available():
+        pytest.skip("the fallback decision is exercised on machines without a GPU")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(2, port, disabled, out), nprocs=2, join=True)
+    for r in range(2):
+        none1, none2, msgs = out[r]
+        assert none1 and none2
+        assert (msgs == []) if disabled else any("peer exchange unavailable" in m for m in msgs)
