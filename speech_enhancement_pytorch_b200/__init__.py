@@ -9,8 +9,10 @@ Public surface (all CUDA-only, no CPU fallback):
     evaluate, segment_stft             src/evaluate.py:10-98,164-183 (segment -> STFT without copies)
     apply_mask, apply_mask_dccrn       model forward tails
     magnitude_feature, stft_custom_with_feature   NN input features
-    loss_mrstft, MRSTFTLoss            loss_function(enhanced, sources) convention
-    ConvSTFT, ConviSTFT                src/model/dccrn.py:669-747
+    loss_mrstft, MRSTFTLoss            loss_function(enhanced, sources) convention; group=... shards the batch over
+                                       GPUs (distributed.peer_exchange: the exchange step over NVLink peer memory)
+    ConvSTFT, ConviSTFT                src/model/dccrn.py:669-747; ConviSTFT.forward_masked = DCCRN tail + iSTFT
+                                       (dccrn.py:203-224) in one launch each way
     enhance                            fused stft_custom -> mask -> istft_custom
     apply_mask_istft                   fused model tail -> istft_custom (masked spectrum never written)
     si_snr, loss_sisdr, SI_SDR         src/loss.py:14-29, src/metric.py:92-123
