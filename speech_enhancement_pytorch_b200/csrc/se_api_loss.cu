@@ -18,30 +18,57 @@ static const int kRes[3][3] = {{512, 128, 512}, {1024, 256, 1024}, {2048, 512, 2
 
 #define SE_DISPATCH_LOSS_GEO(n_fft, CALL)                                              \
     do {                                                                               \
-        if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                      \
+        if (frames8() && n_fft == 512) { using G = Geo<512, 128, 128, 8>; CALL; }      \
+        else if (frames8() && n_fft == 1024) { using G = Geo<1024, 256, 128, 8>; CALL; } \
+        else if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                 \
         else if (n_fft == 1024) { using G = Geo<1024, 256, 256>; CALL; }               \
         else { using G = Geo<2048, 512, 512>; CALL; }                                  \
     } while (0)
 // forward at n = 2048: 8-frame groups halve the working set (64 KB) so that two 256-thread CTAs fit per SM
 #define SE_DISPATCH_LOSS_FWD_GEO(n_fft, CALL)                                          \
     do {                                                                               \
-        if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                      \
+        if (frames8() && n_fft == 512) { using G = Geo<512, 128, 128, 8>; CALL; }      \
+        else if (frames8() && n_fft == 1024) { using G = Geo<1024, 256, 128, 8>; CALL; } \
+        else if (n_fft == 512) { using G = Geo<512, 128, 256>; CALL; }                 \
         else if (n_fft == 1024) { using G = Geo<1024, 256, 256>; CALL; }               \
         else { using G = Geo<2048, 512, 256, 8>; CALL; }                               \
     } while (0)
-static int loss_fwd_frames(int n_fft) { return n_fft >= 2048 ? 8 : 16; }
+static int loss_fwd_frames(int n_fft) { return (engine_version() == 2 || n_fft >= 2048 || frames8()) ? 8 : 16; }
+
+// signal-pair engine (se_kernels2.cuh): forward pairs (reference, estimate) of a row, backward pairs two rows.
+// The backward kernels also hold the right-edge zone in shared memory: tables go undoubled there so that
+// two CTAs (n <= 1024) / one CTA (n = 2048) still fit.
+#define SE_DISPATCH_LOSS_GEO2(n_fft, DUP, CALL)                                        \
+    do {                                                                               \
+        if (n_fft == 512) { using G = Geo2<512, 128, 128, DUP>; CALL; }                \
+        else if (n_fft == 1024) { using G = Geo2<1024, 256, 256, DUP>; CALL; }         \
+        else { using G = Geo2<2048, 512, 512, DUP>; CALL; }                            \
+    } while (0)
+template <class G>
+static cudaError_t run_loss_fwd2(const LossArgs& a, int64_t rows, cudaStream_t st) {
+    return launch(k_loss_fwd2<G>, (unsigned)(rows * a.nchunks), G::NT, Smem2<G>::ANALYSIS, st, a);
+}
+template <class G>
+static cudaError_t run_loss_bwd2(LossArgs a, int64_t rows, cudaStream_t st) {
+    const int64_t prows = (rows + 1) / 2;
+    a.nchunks = plan_synthesis(prows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR, 2, 16);
+    return launch(k_loss_bwd2<G>, (unsigned)(prows * a.nchunks), G::NT, Smem2<G>::FUSED_ADJ, st, a, (int)rows);
+}
 
 template <class G>
 static cudaError_t run_loss_fwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
     return launch(k_loss_fwd<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, st, a);
 }
 template <class G>
-static cudaError_t run_loss_bwd(const LossArgs& a, int64_t rows, cudaStream_t st) {
+static cudaError_t run_loss_bwd(LossArgs a, int64_t rows, cudaStream_t st) {
+    // n = 2048: single-group chunks (16 - (OLA-1) blocks each, no carry); 8-frame groups need >= 2 groups per chunk
+    // so that the reflect fold's sources and destinations share a chunk
+    a.nchunks = G::N >= 2048 ? (a.b_hi + 12) / 13 : plan_synthesis(rows, a.b_hi, G::OLA, G::MINB, G::FR, G::FR == 8 ? 2 : 1, G::FR == 8 ? 16 : 8);
     return launch(k_loss_bwd<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::FUSED_ADJ, st, a);
 }
 template <class G>
 static cudaError_t run_loss_bwd_saved(LossArgs a, int64_t rows, cudaStream_t st) {
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR, G::FR == 8 ? 2 : 1, G::FR == 8 ? 16 : 8);
     return launch(k_loss_bwd_saved<G>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::SYNTH_ADJ, st, a);
 }
 
@@ -113,7 +140,8 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
         a.gpc = gpcs[r]; a.nchunks = nchs[r];
         a.chained = r != 2;
         cudaError_t e;
-        SE_DISPATCH_LOSS_FWD_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
+        if (engine_version() == 2) SE_DISPATCH_LOSS_GEO2(n, true, (e = run_loss_fwd2<G>(a, rows, (cudaStream_t)stream)));
+        else SE_DISPATCH_LOSS_FWD_GEO(n, (e = run_loss_fwd<G>(a, rows, (cudaStream_t)stream)));
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd launch");
     }
     // plain stream serialisation: the reduction needs ALL three kernels, not just its immediate predecessor
@@ -156,9 +184,9 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
         a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
         a.inv_res = 1.0f / 3.0f;
         cudaError_t e;
-        if (loss_recompute()) {
-            a.nchunks = n >= 2048 ? (a.b_hi + 12) / 13      // single-group chunks: 16 - (OLA-1) blocks each, no carry
-                                  : plan_synthesis(rows, a.b_hi, n / hop, 2, 16);
+        if (loss_recompute() && engine_version() == 2) {
+            SE_DISPATCH_LOSS_GEO2(n, false, (e = run_loss_bwd2<G>(a, rows, (cudaStream_t)stream)));
+        } else if (loss_recompute()) {
             SE_DISPATCH_LOSS_GEO(n, (e = run_loss_bwd<G>(a, rows, (cudaStream_t)stream)));
         } else {
             a.estspec = const_cast<float2*>(reinterpret_cast<const float2*>(refmag0 + loss_refmag_region_floats(rows, nsample))) +

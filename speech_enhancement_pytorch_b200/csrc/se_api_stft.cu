@@ -11,9 +11,74 @@ static cudaError_t run_analysis(AnaArgs a, int64_t rows, cudaStream_t st) {
 }
 template <class G, int EMODE>
 static cudaError_t run_synthesis(SynArgs a, int64_t rows, cudaStream_t st) {
-    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR);
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR, (EMODE == EMIT_ADJ && G::FR == 8) ? 2 : 1, G::FR == 8 ? 16 : 8);
     return launch(k_synthesis<G, EMODE>, (unsigned)(rows * a.nchunks), G::NT,
                   EMODE == EMIT_ADJ ? Smem<G>::SYNTH_ADJ : Smem<G>::SYNTH_ISTFT, st, a);
+}
+
+// ---- signal-pair engine (two rows per CTA).  Tables are staged doubled when MINB CTAs still fit, undoubled
+// otherwise; geometries that fit neither way stay on the scalar engine (returns false).
+template <class G> constexpr bool fits2(size_t bytes) { return bytes <= 232448 && G::MINB * (bytes + 1024) <= 233472; }
+
+template <int N, int HOP, int NT, int LMODE>
+static bool run_analysis2(AnaArgs a, int64_t rows, cudaStream_t st, cudaError_t& e) {
+    using GD = Geo2<N, HOP, NT, true>;
+    using GN = Geo2<N, HOP, NT, false>;
+    const int64_t prows = (rows + 1) / 2;
+    plan_analysis(prows, a.nframe, a.gpc, a.nchunks, 8);
+    if constexpr (fits2<GD>(Smem2<GD>::ANALYSIS)) {
+        e = launch(k_analysis2<GD, LMODE>, (unsigned)(prows * a.nchunks), NT, Smem2<GD>::ANALYSIS, st, a, (int)rows);
+        return true;
+    } else if constexpr (Smem2<GN>::ANALYSIS <= 232448) {        // undoubled tables, possibly one CTA fewer per SM
+        e = launch(k_analysis2<GN, LMODE>, (unsigned)(prows * a.nchunks), NT, Smem2<GN>::ANALYSIS, st, a, (int)rows);
+        return true;
+    }
+    return false;
+}
+template <int N, int HOP, int NT, int EMODE>
+static bool run_synthesis2(SynArgs a, int64_t rows, cudaStream_t st, cudaError_t& e) {
+    using GD = Geo2<N, HOP, NT, true>;
+    using GN = Geo2<N, HOP, NT, false>;
+    const int64_t prows = (rows + 1) / 2;
+    constexpr bool ADJ = EMODE == EMIT_ADJ;
+    a.nchunks = plan_synthesis(prows, a.b_hi - a.b_lo, GD::OLA, GD::MINB, 8, ADJ ? 2 : 1, 16);
+    constexpr size_t BD = ADJ ? Smem2<GD>::SYNTH_ADJ : Smem2<GD>::SYNTH_ISTFT;
+    constexpr size_t BN = ADJ ? Smem2<GN>::SYNTH_ADJ : Smem2<GN>::SYNTH_ISTFT;
+    if constexpr (fits2<GD>(BD)) {
+        e = launch(k_synthesis2<GD, EMODE>, (unsigned)(prows * a.nchunks), NT, BD, st, a, (int)rows);
+        return true;
+    } else if constexpr (BN <= 232448) {
+        e = launch(k_synthesis2<GN, EMODE>, (unsigned)(prows * a.nchunks), NT, BN, st, a, (int)rows);
+        return true;
+    }
+    return false;
+}
+// CALL sees the compile-time constants N2, HOP2, NT2
+#define SE_DISPATCH_GEO2(n_fft, hop, CALL)                                                              \
+    do {                                                                                                \
+        if (n_fft == 512 && hop == 128) { constexpr int N2 = 512, HOP2 = 128, NT2 = 128; CALL; }        \
+        else if (n_fft == 512 && hop == 256) { constexpr int N2 = 512, HOP2 = 256, NT2 = 128; CALL; }   \
+        else if (n_fft == 1024 && hop == 256) { constexpr int N2 = 1024, HOP2 = 256, NT2 = 256; CALL; } \
+        else if (n_fft == 1024 && hop == 512) { constexpr int N2 = 1024, HOP2 = 512, NT2 = 256; CALL; } \
+        else if (n_fft == 2048 && hop == 512) { constexpr int N2 = 2048, HOP2 = 512, NT2 = 512; CALL; } \
+        else { constexpr int N2 = 2048, HOP2 = 1024, NT2 = 512; CALL; }                                 \
+    } while (0)
+
+template <int LMODE>
+static cudaError_t dispatch_analysis(const AnaArgs& a, int64_t rows, int n_fft, int hop, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    bool done = false;
+    if (engine_version() == 2) SE_DISPATCH_GEO2(n_fft, hop, (done = run_analysis2<N2, HOP2, NT2, LMODE>(a, rows, st, e)));
+    if (!done) SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LMODE>(a, rows, st)));
+    return e;
+}
+template <int EMODE>
+static cudaError_t dispatch_synthesis(const SynArgs& a, int64_t rows, int n_fft, int hop, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    bool done = false;
+    if (engine_version() == 2) SE_DISPATCH_GEO2(n_fft, hop, (done = run_synthesis2<N2, HOP2, NT2, EMODE>(a, rows, st, e)));
+    if (!done) SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMODE>(a, rows, st)));
+    return e;
 }
 
 extern "C" {
@@ -27,8 +92,7 @@ int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int 
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
     a.in = x; a.out = spec; a.in_stride = nsample; a.seg_rows = 1; a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
-    cudaError_t e;
-    SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
+    const cudaError_t e = dispatch_analysis<LOAD_REFLECT>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_fwd launch");
 }
 
@@ -72,8 +136,7 @@ int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t ncli
     a.in = x; a.out = spec; a.in_stride = seg_stride; a.clip_stride = clip_stride; a.seg_rows = (int)nclip;
     a.clip_len = (int)clip_len; a.nsample = (int)nsample; a.in_len = (int)nsample;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
-    cudaError_t e;
-    SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));
+    const cudaError_t e = dispatch_analysis<LOAD_REFLECT>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_segments_fwd launch");
 }
 
@@ -88,8 +151,7 @@ int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, in
     a.nframe = (int)(1 + nsample / hop);
     a.b_lo = 0; a.b_hi = (int)((nsample + n_fft + hop - 1) / hop);
     a.accumulate = accumulate; a.edge_scale = 2.0f;
-    cudaError_t e;
-    SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMIT_ADJ>(a, rows, (cudaStream_t)stream)));
+    const cudaError_t e = dispatch_synthesis<EMIT_ADJ>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_bwd launch");
 }
 
@@ -106,8 +168,7 @@ int se_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int6
     a.nframe = (int)nframe;
     a.b_lo = (n_fft / 2) / hop; a.b_hi = (int)((n_fft / 2 + length + hop - 1) / hop);
     a.accumulate = 0; a.edge_scale = 1.0f;
-    cudaError_t e;
-    SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMIT_ISTFT>(a, rows, (cudaStream_t)stream)));
+    const cudaError_t e = dispatch_synthesis<EMIT_ISTFT>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_istft_fwd launch");
 }
 
@@ -120,8 +181,7 @@ int se_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, in
     if (int rc = get_tables(n_fft, hop, win_length, false, scale / (float)n_fft, a.tb)) return rc;
     a.in = gy; a.out = gspec; a.in_stride = length; a.seg_rows = 1; a.in_len = (int)length;
     a.nsample = (int)(n_fft + hop * (nframe - 1)); a.nframe = (int)nframe; a.pad = 0; a.edge_scale = 0.5f;
-    cudaError_t e;
-    SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_ENV>(a, rows, (cudaStream_t)stream)));
+    const cudaError_t e = dispatch_analysis<LOAD_ENV>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_istft_bwd launch");
 }
 

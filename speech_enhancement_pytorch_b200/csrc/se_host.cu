@@ -133,6 +133,27 @@ static bool envelope_ok_uncached(int n, int hop, int win_len, bool front, int64_
     return true;
 }
 
+int engine_version() {
+    auto read = [] { const char* e = std::getenv("SE_ENGINE"); return (e && e[0] == '2') ? 2 : 1; };
+#ifdef SE_EMULATE
+    return read();           // tests flip it between calls
+#else
+    static const int v = read();
+    return v;
+#endif
+}
+
+// SE_FR8=1: 8-frame groups (half the working set, twice the CTAs per SM) for the scalar engine's n <= 1024 kernels
+int frames8() {
+    auto read = [] { const char* e = std::getenv("SE_FR8"); return (e && e[0] == '1') ? 1 : 0; };
+#ifdef SE_EMULATE
+    return read();
+#else
+    static const int v = read();
+    return v;
+#endif
+}
+
 // ------------------------------------------------------------------ launch planning
 static int g_target_ctas = 148 * 8;
 
@@ -146,14 +167,16 @@ void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_p
 // Pick the groups-per-chunk g that minimises (waves x g): a chunk of g groups emits 16 g - (ola-1)
 // blocks (the first ola-1 frames are halo recompute), so larger g wastes less, but the grid must still
 // fill the GPU in whole waves.  ctas_per_sm = resident CTAs of this kernel per SM.
-int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group) {
+int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group, int g_min, int g_max) {
     const int64_t slots = 148LL * (ctas_per_sm > 0 ? ctas_per_sm : 1);
     int best_chunks = 1;
     double best_cost = 1e30;
     // SE_FORCE_GROUPS=g pins the choice (tests exercise the multi-group carry path on tiny inputs)
     const char* force = std::getenv("SE_FORCE_GROUPS");
-    const int g_lo = force ? std::atoi(force) : 1, g_hi = force ? std::atoi(force) : 8;
-    for (int g = (g_lo < 1 ? 1 : g_lo); g <= (g_hi > 8 ? 8 : g_hi); ++g) {
+    int g_lo = force ? std::atoi(force) : g_min, g_hi = force ? std::atoi(force) : g_max;
+    g_lo = g_lo < g_min ? g_min : g_lo;
+    g_hi = g_hi > g_max ? g_max : (g_hi < g_lo ? g_lo : g_hi);
+    for (int g = g_lo; g <= g_hi; ++g) {
         const int cb_max = frames_per_group * g - (ola - 1);
         const int nchunks = (nb + cb_max - 1) / cb_max;
         const int cb = (nb + nchunks - 1) / nchunks;                 // even split (make_chunk)

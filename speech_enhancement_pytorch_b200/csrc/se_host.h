@@ -1,7 +1,7 @@
 // se_host.h -- host-side helpers shared by the C-ABI translation units (se_api_*.cu).
 #pragma once
 #include "../../include/se_b200.h"
-#include "se_kernels.cuh"
+#include "se_kernels2.cuh"
 
 #include <string>
 
@@ -16,7 +16,12 @@ int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out
 // torch.istft's "window overlap add min" check on the host (no device sync)
 bool envelope_ok(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_);
 void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_per_group);
-int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group);
+// g_min..g_max: groups per chunk considered (the pair engine's adjoint emitters need chunks of >= 7 blocks: g_min = 2)
+int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_per_group, int g_min = 1, int g_max = 8);
+// SE_ENGINE=2 selects the signal-pair engine (se_fft2.cuh) where both exist; default 1: the scalar engine, which
+// measured faster on B200 (profiles/r02_notes.md)
+int engine_version();
+int frames8();
 int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length);
 
 // MODE (0..3) x TANH -> compile-time template arguments
@@ -35,7 +40,9 @@ int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_leng
 
 #define SE_DISPATCH_GEO(n_fft, hop, CALL)                                              \
     do {                                                                               \
-        if (n_fft == 512 && hop == 128) { using G = Geo<512, 128, 256>; CALL; }        \
+        if (frames8() && n_fft == 512 && hop == 128) { using G = Geo<512, 128, 128, 8>; CALL; }        \
+        else if (frames8() && n_fft == 1024 && hop == 256) { using G = Geo<1024, 256, 128, 8>; CALL; } \
+        else if (n_fft == 512 && hop == 128) { using G = Geo<512, 128, 256>; CALL; }   \
         else if (n_fft == 512 && hop == 256) { using G = Geo<512, 256, 256>; CALL; }   \
         else if (n_fft == 1024 && hop == 256) { using G = Geo<1024, 256, 256>; CALL; } \
         else if (n_fft == 1024 && hop == 512) { using G = Geo<1024, 512, 256>; CALL; } \

@@ -406,3 +406,28 @@ def test_emu_overlap_and_add_matches_reference_golden_and_autograd(tag):
     st = torch.from_numpy(rows).requires_grad_(True)
     (gw,) = torch.autograd.grad(oref.overlap_and_add_ref(st, step), st, torch.from_numpy(go))
     assert np.array_equal(E.overlap_add_bwd(go, frames, length, step), gw.numpy())
+
+
+# ---------------------------------------------------------------- signal-pair engine (se_fft2.cuh / se_kernels2.cuh)
+@pytest.mark.parametrize("rows,N,groups", [(3, 6001, None), (1, 4100, "2"), (2, 9000, "3")])
+def test_emu_pair_engine_loss_odd_rows_ragged_and_carry(rows, N, groups, monkeypatch):
+    """Odd row counts (the last row is paired with itself), lengths that are no multiple of any hop, and
+    multi-group chunks (OLA carry across 8-frame groups) through the pair-engine loss kernels; the scalar
+    engine (SE_ENGINE=1) must agree with it to fp32 round-off."""
+    if groups:
+        monkeypatch.setenv("SE_FORCE_GROUPS", groups)
+    rng = np.random.default_rng(rows * 7 + N)
+    ref = rng.standard_normal((rows, N)).astype(np.float32)
+    est = (ref + 0.1 * rng.standard_normal((rows, N))).astype(np.float32)
+    l64, g64 = o64.mrstft_loss(est, ref, with_grad=True)
+    out = {}
+    for eng in ("2", "1"):
+        monkeypatch.setenv("SE_ENGINE", eng)
+        sums, loss = E.mrstft_fwd(est, ref)
+        g = E.mrstft_bwd(est, ref, sums, 1.0)
+        assert not np.isnan(g).any()
+        assert abs(loss - l64) / l64 < 1e-5
+        assert rel(g, g64) < 1e-3
+        out[eng] = (sums.copy(), g.copy())
+    assert rel(out["2"][0], out["1"][0]) < 1e-5
+    assert rel(out["2"][1], out["1"][1]) < 1e-3      # both sit within 1e-3 of float64; the gradient is ill-conditioned
