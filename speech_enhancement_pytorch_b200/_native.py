@@ -15,7 +15,9 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 LIB_PATH = os.path.join(_PKG, "libse_b200.so")
+TORCH_LIB_PATH = os.path.join(_PKG, "libse_b200_torch.so")      # TORCH_LIBRARY(se_b200) + C++ autograd over the C-ABI
 CSRC = os.path.join(_PKG, "csrc")
+CSRC_TORCH = os.path.join(_PKG, "csrc_torch")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -53,10 +55,42 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
 
 
+def _torch_sources():
+    return sorted(os.path.join(CSRC_TORCH, f) for f in os.listdir(CSRC_TORCH) if f.endswith(".cpp"))
+
+
+def needs_torch_build() -> bool:
+    if not os.path.exists(TORCH_LIB_PATH):
+        return True
+    t = os.path.getmtime(TORCH_LIB_PATH)
+    deps = _torch_sources() + [os.path.join(_ROOT, "include", "se_b200.h")]
+    return any(os.path.getmtime(p) > t for p in deps)
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """g++ the PyTorch C++ extension (csrc_torch/*.cpp: operator registrations + C++ autograd nodes, no kernels)
+    against the torch headers and link it to the in-tree libse_b200.so."""
+    if not (force or needs_torch_build()):
+        return TORCH_LIB_PATH
+    from torch.utils import cpp_extension as ce
+    libdir = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared",
+           "-D_GLIBCXX_USE_CXX11_ABI=" + str(int(torch._C._GLIBCXX_USE_CXX11_ABI))]
+    cmd += [f"-I{p}" for p in ce.include_paths()] + [f"-I{cuda_inc}"] + _torch_sources()
+    cmd += ["-o", TORCH_LIB_PATH, f"-L{_PKG}", "-lse_b200", f"-L{libdir}", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda",
+            "-ltorch_cuda", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ (torch extension) failed:\n" + res.stdout + res.stderr)
+    return TORCH_LIB_PATH
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a with nvcc (one process per translation unit, in parallel) and
     link the in-tree libse_b200.so."""
     if not (force or needs_build()):
+        build_torch_ext(force=False)
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -81,6 +115,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         with open(os.path.join(BUILD_DIR, "ptxas.log"), "w") as f:
             f.write(log)
+    build_torch_ext(force=True)
     return LIB_PATH
 
 
@@ -147,6 +182,26 @@ def lib():
             L.se_mrstft_exchange_value.argtypes = [_PTR, _c.POINTER(_PTR), _INT, _INT, _I64, _I64, _PTR, _PTR]
             _lib = L
     return _lib
+
+
+_torch_ops = None
+
+
+def torch_ops():
+    """torch.ops.se_b200 (the C++ extension).  Fails loudly when it has not been built: there is no Python or
+    PyTorch fallback for these operators."""
+    global _torch_ops
+    if _torch_ops is None:
+        lib()                                           # libse_b200.so first (the extension links against it)
+        with _lock:
+            if _torch_ops is None:
+                if not os.path.exists(TORCH_LIB_PATH):
+                    raise RuntimeError(
+                        f"{TORCH_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`.  "
+                        "This package has no CPU or PyTorch fallback.")
+                torch.ops.load_library(TORCH_LIB_PATH)
+                _torch_ops = torch.ops.se_b200
+    return _torch_ops
 
 
 class SEError(RuntimeError):

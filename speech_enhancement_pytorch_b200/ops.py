@@ -1,5 +1,9 @@
 """Row-level ops over the C-ABI, with autograd.  Shapes are already flattened to rows here;
 the reference-facing signatures live in evaluate.py / masking.py / loss.py / dccrn.py.
+
+The step's hot operators (stft / istft / mask / mask+istft tail / enhance / single-process MR-STFT loss) go through the
+PyTorch C++ extension (csrc_torch/se_torch.cpp: TORCH_LIBRARY(se_b200) + C++ autograd nodes over the same C-ABI);
+the remaining operators bind the C-ABI with ctypes and Python autograd.Functions.
 """
 from __future__ import annotations
 
@@ -65,30 +69,6 @@ def istft_rows_adjoint(gy, nframe, n_fft, hop, win_length, scale):
 
 
 # ------------------------------------------------------------------ autograd
-class _STFT(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, n_fft, hop, win_length, scale):
-        ctx.cfg = (x.shape[1], n_fft, hop, win_length, scale)
-        return stft_rows(x, n_fft, hop, win_length, scale)
-
-    @staticmethod
-    def backward(ctx, g):
-        n, n_fft, hop, win_length, scale = ctx.cfg
-        return stft_rows_adjoint(g.contiguous(), n, n_fft, hop, win_length, scale), None, None, None, None
-
-
-class _ISTFT(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, spec, length, n_fft, hop, win_length, scale):
-        ctx.cfg = (spec.shape[2], n_fft, hop, win_length, scale)
-        return istft_rows(spec, length, n_fft, hop, win_length, scale)
-
-    @staticmethod
-    def backward(ctx, g):
-        nt, n_fft, hop, win_length, scale = ctx.cfg
-        return istft_rows_adjoint(g.contiguous(), nt, n_fft, hop, win_length, scale), None, None, None, None, None
-
-
 def _as_f32(t):
     if t.dtype in (torch.float16, torch.bfloat16):
         return t.float()          # spectra stay fp32 under a bf16/fp16 model (BASELINE config 4)
@@ -100,45 +80,12 @@ def _needs_grad(*tensors):
 
 
 def stft(x_rows, n_fft, hop, win_length, scale):
-    _check_cfg(n_fft, hop, win_length)
-    x = _as_f32(x_rows).contiguous()
-    if not _needs_grad(x):                      # inference / no-grad inputs: skip the autograd node
-        return stft_rows(x, n_fft, hop, win_length, float(scale))
-    return _STFT.apply(x, n_fft, hop, win_length, float(scale))
+    # C++ op: config check, fp16/bf16 up-cast, contiguity, autograd node only when a gradient is needed
+    return nv.torch_ops().stft(x_rows, n_fft, hop, win_length, float(scale))
 
 
 def istft(spec_rows, length, n_fft, hop, win_length, scale):
-    _check_cfg(n_fft, hop, win_length)
-    spec = _as_f32(spec_rows).contiguous()
-    if not _needs_grad(spec):
-        return istft_rows(spec, int(length), n_fft, hop, win_length, float(scale))
-    return _ISTFT.apply(spec, int(length), n_fft, hop, win_length, float(scale))
-
-
-class _Mask(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, spec, mask, mode, pre_tanh):
-        nv.require_cuda_f32(spec, mask)
-        out = torch.empty_like(spec)
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_mask_fwd(spec.data_ptr(), mask.data_ptr(), out.data_ptr(), spec.numel() // 2,
-                                          mode, int(pre_tanh), nv.stream_ptr(spec.device)))
-        ctx.save_for_backward(spec, mask)
-        ctx.cfg = (mode, pre_tanh)
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        spec, mask = ctx.saved_tensors
-        mode, pre_tanh = ctx.cfg
-        g = g.contiguous()
-        gmask = torch.empty_like(mask)
-        gspec = torch.empty_like(spec) if ctx.needs_input_grad[0] else None
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_mask_bwd(spec.data_ptr(), mask.data_ptr(), g.data_ptr(), gmask.data_ptr(),
-                                          _ptr(gspec), spec.numel() // 2, mode, int(pre_tanh),
-                                          nv.stream_ptr(spec.device)))
-        return gspec, gmask, None, None
+    return nv.torch_ops().istft(spec_rows, int(length), n_fft, hop, win_length, float(scale))
 
 
 class _MaskPlanar(torch.autograd.Function):
@@ -192,7 +139,7 @@ def mask_apply(spec, mask, mode, pre_tanh=False):
     want = spec.shape[:-1] if mode == "real" else spec.shape
     if tuple(mask.shape) != tuple(want):
         raise ValueError(f"mask shape {tuple(mask.shape)} does not match spectrum {tuple(spec.shape)} for mode {mode}")
-    return _Mask.apply(_as_f32(spec).contiguous(), _as_f32(mask).contiguous(), nv.MASK_MODES[mode], bool(pre_tanh))
+    return nv.torch_ops().mask(spec, mask, nv.MASK_MODES[mode], bool(pre_tanh))
 
 
 class _MRSTFT(torch.autograd.Function):
@@ -241,6 +188,8 @@ class _MRSTFT(torch.autograd.Function):
 def mrstft_loss_rows(est_rows, ref_rows, group=None, global_rows=None):
     if ref_rows.requires_grad:
         raise NotImplementedError("loss_mrstft: gradient flows to `enhanced` only (targets must not require grad)")
+    if group is None:
+        return nv.torch_ops().mrstft_loss(est_rows, ref_rows)
     return _MRSTFT.apply(_as_f32(est_rows).contiguous(), _as_f32(ref_rows).contiguous(), group, global_rows)
 
 
@@ -360,78 +309,11 @@ def psa_loss(enh, tgt, mix, group=None):
 
 
 # ------------------------------------------------------------------ fused enhance
-class _Enhance(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, mask, n_fft, hop, win_length, mode, pre_tanh):
-        nv.require_cuda_f32(x, mask)
-        rows, n = x.shape
-        y = torch.empty_like(x)
-        with nv.on_device(x.device):
-            nv.check(nv.lib().se_enhance_fwd(x.data_ptr(), mask.data_ptr(), y.data_ptr(), rows, n, n_fft, hop,
-                                             win_length, mode, int(pre_tanh), nv.stream_ptr(x.device)))
-        ctx.save_for_backward(x, mask)
-        ctx.cfg = (n_fft, hop, win_length, mode, pre_tanh)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, mask = ctx.saved_tensors
-        n_fft, hop, win_length, mode, pre_tanh = ctx.cfg
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("enhance: gradient wrt the input waveform is not built")
-        rows, n = x.shape
-        gy = gy.contiguous()
-        gmask = torch.empty_like(mask)
-        if n_fft > 1024:
-            # two 2048-point working sets do not fit one SM's shared memory: compose our own kernels
-            spec = stft_rows(x, n_fft, hop, win_length, 1.0 / win_length)
-            gspec = istft_rows_adjoint(gy, spec.shape[2], n_fft, hop, win_length, float(win_length))
-            with nv.on_device(x.device):
-                nv.check(nv.lib().se_mask_bwd(spec.data_ptr(), mask.data_ptr(), gspec.data_ptr(), gmask.data_ptr(), 0,
-                                              spec.numel() // 2, mode, int(pre_tanh), nv.stream_ptr(x.device)))
-            return None, gmask, None, None, None, None, None
-        with nv.on_device(x.device):
-            nv.check(nv.lib().se_enhance_bwd(gy.data_ptr(), x.data_ptr(), mask.data_ptr(), gmask.data_ptr(), rows, n,
-                                             n_fft, hop, win_length, mode, int(pre_tanh), nv.stream_ptr(x.device)))
-        return None, gmask, None, None, None, None, None
-
-
 def enhance_rows(x_rows, mask_rows, n_fft, hop, win_length, mode, pre_tanh=False):
     _check_cfg(n_fft, hop, win_length)
     if mode not in nv.MASK_MODES:
         raise ValueError(f"unknown masking mode {mode!r}")
-    return _Enhance.apply(_as_f32(x_rows).contiguous(), _as_f32(mask_rows).contiguous(), n_fft, hop, win_length,
-                          nv.MASK_MODES[mode], bool(pre_tanh))
-
-
-class _MaskISTFT(torch.autograd.Function):
-    """istft_custom(apply_mask(spec, mask)) in one launch each way; the masked spectrum and its gradient stay
-    in registers.  Gradient flows to the raw mask only (spec = stft_custom(mixture) is data)."""
-
-    @staticmethod
-    def forward(ctx, spec, mask, length, n_fft, hop, win_length, scale, mode, pre_tanh):
-        nv.require_cuda_f32(spec, mask)
-        rows, nf, nt, _ = spec.shape
-        y = torch.empty((rows, length), dtype=torch.float32, device=spec.device)
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_mask_istft_fwd(spec.data_ptr(), mask.data_ptr(), y.data_ptr(), rows, nt, length, n_fft,
-                                                hop, win_length, scale, mode, int(pre_tanh), nv.stream_ptr(spec.device)))
-        ctx.save_for_backward(spec, mask)
-        ctx.cfg = (length, n_fft, hop, win_length, scale, mode, pre_tanh)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        spec, mask = ctx.saved_tensors
-        length, n_fft, hop, win_length, scale, mode, pre_tanh = ctx.cfg
-        rows, nf, nt, _ = spec.shape
-        gy = gy.contiguous()
-        gmask = torch.empty_like(mask)
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_mask_istft_bwd(gy.data_ptr(), spec.data_ptr(), mask.data_ptr(), gmask.data_ptr(), rows,
-                                                nt, length, n_fft, hop, win_length, scale, mode, int(pre_tanh),
-                                                nv.stream_ptr(spec.device)))
-        return None, gmask, None, None, None, None, None, None, None
+    return nv.torch_ops().enhance(x_rows, mask_rows, n_fft, hop, win_length, nv.MASK_MODES[mode], bool(pre_tanh))
 
 
 def mask_istft_rows(spec, mask, length, n_fft, hop, win_length, scale, mode, pre_tanh=False):
@@ -442,8 +324,8 @@ def mask_istft_rows(spec, mask, length, n_fft, hop, win_length, scale, mode, pre
     if spec.requires_grad:
         # the spectrum itself is being trained through: keep the two differentiable stages separate
         return istft(mask_apply(spec, mask, mode, pre_tanh), length, n_fft, hop, win_length, scale)
-    return _MaskISTFT.apply(_as_f32(spec).contiguous(), _as_f32(mask).contiguous(), int(length), n_fft, hop, win_length,
-                            float(scale), nv.MASK_MODES[mode], bool(pre_tanh))
+    return nv.torch_ops().mask_istft(spec, mask, int(length), n_fft, hop, win_length, float(scale), nv.MASK_MODES[mode],
+                                     bool(pre_tanh))
 
 
 class _OverlapAdd(torch.autograd.Function):

@@ -48,3 +48,19 @@ def test_argument_errors_do_not_need_a_gpu():
     assert L.se_stft_fwd(p, p, 1, 4096, 512, 100, 512, 1.0, None) == -2
     assert L.se_istft_fwd(p, p, 1, 0, 100, 512, 128, 512, 1.0, None) == -1
     assert L.se_mask_fwd(p, p, p, 4, 7, 0, None) == -2
+
+
+def test_torch_extension_registers_the_operators():
+    """The PyTorch C++ extension (TORCH_LIBRARY(se_b200), csrc_torch/se_torch.cpp) loads without a GPU and exposes
+    the step's operators; calling one on a CPU tensor raises instead of falling back."""
+    import pytest
+    import torch
+    from speech_enhancement_pytorch_b200 import _native as nv
+    ops = nv.torch_ops()
+    for name in ("stft", "istft", "mask", "mask_istft", "enhance", "mrstft_loss"):
+        assert hasattr(ops, name), name
+    assert "Tensor x, int n_fft, int hop, int win_length, float scale" in str(torch.ops.se_b200.stft.default._schema)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.mrstft_loss(torch.zeros(1, 4096), torch.zeros(1, 4096))
+    with pytest.raises(NotImplementedError):
+        ops.istft(torch.zeros(1, 161, 5, 2), 640, 320, 80, 320, 320.0)
