@@ -552,6 +552,35 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         rounds_ms.append(float(ms) / args.steps)
     ms_per_step = sorted(rounds_ms)[len(rounds_ms) // 2]
+    # ---- N > 1: the sharded loss (9-double exchange step) must equal the single-GPU loss over the concatenated batch.
+    # Every rank's first input set is regenerated from its seed on rank 0 (the driver's box has the GPUs the 2-rank
+    # pytest cases need, but runs them on one): printed in the line, and the run fails if they disagree.
+    shard_check = None
+    if group is not None:
+        xs, cs = sets[0][0], sets[0][1]
+        est = xs.reshape(rows, 1, N).clone().requires_grad_(True)
+        l_sh = se.loss_mrstft(est, cs.reshape(rows, 1, N), group)
+        (g_sh,) = torch.autograd.grad(l_sh, est)
+        if rank == 0:
+            allx, allc = [], []
+            for r in range(world):
+                gr = torch.Generator(device="cpu").manual_seed(1235 + r)
+                xr = torch.randn(rows, N, generator=gr)
+                allx.append(xr)
+                allc.append(xr + 0.3 * torch.randn(rows, N, generator=gr))
+            e1 = torch.cat(allx).reshape(rows * world, 1, N).to(dev).requires_grad_(True)
+            l_1 = se.loss_mrstft(e1, torch.cat(allc).reshape(rows * world, 1, N).to(dev))
+            (g_1,) = torch.autograd.grad(l_1, e1)
+            gd = float((g_sh - g_1[:rows]).abs().max() / g_1[:rows].abs().max())
+            shard_check = {"loss_sharded": float(l_sh), "loss_single_gpu": float(l_1),
+                           "rel_diff": abs(float(l_sh) - float(l_1)) / abs(float(l_1)), "grad_rel_diff_rank0_rows": gd,
+                           "what": f"loss_mrstft over {world} ranks x {rows} rows vs one GPU on all {rows * world} rows, same inputs"}
+            assert shard_check["rel_diff"] < 1e-6 and gd < 1e-5, shard_check
+            del e1, g_1, allx, allc
+        del est, g_sh
+        torch.cuda.empty_cache()
+        sync_all()
+
     # the other compositions, same timing rules, for context
     audio_s = rows * world * N / SR
     alts = []
@@ -836,7 +865,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "rounds_ms_per_step": [round(v, 5) for v in rounds_ms], "timing": "median of rounds",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, exchange),
-        "clocks": clocks, "e2e": e2e, "configs": configs, "incumbent": incumbent, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
+        "clocks": clocks, "e2e": e2e, "configs": configs, "incumbent": incumbent, "sharded_loss_check": shard_check, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
         "composition": comp, "alt_compositions": alts,
         "loss": loss_val, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))

@@ -199,7 +199,136 @@ def gen_tasnet_and_metric():
     save("tasnet_metric", **out)
 
 
+def _stub_missing_third_party():
+    """src.distrib / src.dataset / src.utils import omegaconf, julius, librosa, ... at module level (absent here and
+    unused by collate_fn_pad): any import of those names resolves to an empty stub package, for the import only."""
+    import importlib.abc
+    import importlib.machinery
+    import types
+
+    class Stub(types.ModuleType):
+        def __getattr__(self, k):
+            if k.startswith("__"):
+                raise AttributeError(k)
+            m = Stub(self.__name__ + "." + k)
+            setattr(self, k, m)
+            return m
+
+        def __call__(self, *a, **k):
+            return None
+
+    class Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+        MISSING = ("omegaconf", "julius", "librosa", "pesq", "pypesq", "pystoi", "museval", "clarity", "soundfile",
+                   "torchaudio", "hydra", "tensorboard")
+
+        def find_spec(self, name, path, target=None):
+            if name.split(".")[0] in self.MISSING:
+                return importlib.machinery.ModuleSpec(name, self, is_package=True)
+
+        def create_module(self, spec):
+            return Stub(spec.name)
+
+        def exec_module(self, module):
+            pass
+
+    if not any(type(f).__name__ == "Finder" for f in sys.meta_path):
+        sys.meta_path.append(Finder())
+
+
+def gen_losses_evaluate_collate_features():
+    """The "next" rows of SURVEY 8f from the REAL reference: src.loss (si_snr, loss_sisdr, PSA: src/loss.py:14-56),
+    src.evaluate.evaluate with model=None (src/evaluate.py:10-98), collate_fn_pad (src/distrib.py:38-98) and the
+    models' magnitude features (Amplitude module dcunet.py:372-379; unet.py:40, dnn.py:98, crn.py:101 captured with a
+    forward pre-hook on the first layer of a real model forward)."""
+    from src.loss import si_snr, loss_sisdr, loss_phase_sensitive_spectral_approximation
+    from src.evaluate import evaluate
+    g = torch.Generator().manual_seed(4711)
+    out = {}
+    # --- SI-SNR: a few shapes, incl. near-silent targets
+    for tag, shape in {"a": (4, 1, 3000), "b": (2, 2, 1, 1777), "c": (3, 8000)}.items():
+        s2 = torch.randn(*shape, generator=g)
+        s1 = s2 + 0.5 * torch.randn(*shape, generator=g)
+        out[f"sisnr_s1_{tag}"], out[f"sisnr_s2_{tag}"] = s1, s2
+        out[f"sisnr_{tag}"] = si_snr(s1, s2)
+        out[f"sisdr_loss_{tag}"] = loss_sisdr(s1, s2)
+    # --- PSA on three spectra
+    enh, tgt, mix = (torch.randn(2, 1, 257, 40, 2, generator=g) for _ in range(3))
+    out["psa_enh"], out["psa_tgt"], out["psa_mix"] = enh, tgt, mix
+    out["psa"] = loss_phase_sensitive_spectral_approximation(enh, tgt, mix)
+    save("losses", **out)
+
+    # --- evaluate(model=None): z-score and no normalisation, lengths that do / do not need the zero-filled tail
+    out = {}
+    for tag, (shape, norm, n_fft, hop, segment) in {
+            "zscore": ((1, 2, 5000), "z-score", 512, 128, 0.128), "plain": ((2, 1, 4096), "none", 512, 128, 0.128),
+            "n1024": ((1, 1, 9000), "z-score", 1024, 256, 0.256)}.items():
+        mixture = 0.3 * torch.randn(*shape, generator=g) + 0.05
+        conf = SimpleNamespace(dset=SimpleNamespace(norm=norm, sample_rate=16000),
+                               model=SimpleNamespace(name="unet", n_fft=n_fft, hop_length=hop, win_length=n_fft, center=True,
+                                                     segment=segment, sources=["clean"]))
+        out[f"mix_{tag}"] = mixture
+        out[f"enh_{tag}"] = evaluate(mixture, None, "cpu", conf)
+        out[f"meta_{tag}"] = np.array([n_fft, hop, int(16000 * segment), 1 if norm == "z-score" else 0])
+    save("evaluate", **out)
+
+    # --- collate_fn_pad
+    _stub_missing_third_party()
+    from src.distrib import collate_fn_pad
+    out = {}
+    conf = SimpleNamespace(segment=0.25, sample_rate=8000)          # 2000-sample segments
+    lengths = [4100, 1500, 2000, 6001]
+    batch = []
+    for i, n in enumerate(lengths):
+        mixture = torch.randn(2, n, generator=g)
+        sources = torch.randn(1, 2, n, generator=g)
+        batch.append((mixture, sources, {"i": i}, {"i": i}, f"clip{i}"))
+        out[f"mix_{i}"], out[f"src_{i}"] = mixture, sources
+    for tag, drop in (("drop", True), ("pad", False)):
+        bm, bs, _, _, _, index_batch = collate_fn_pad(conf, drop_last=drop)(batch)
+        out[f"batch_mix_{tag}"], out[f"batch_src_{tag}"], out[f"index_{tag}"] = bm, bs, np.array(index_batch)
+    out["segment_length"] = np.array(2000)
+    save("collate", **out)
+
+    # --- magnitude features from real model forwards
+    from src.model.dcunet import Amplitude
+    from src.model.unet import UNet
+    from src.model.dnn import DeepNeuralNetwork
+    from src.model.crn import CRN
+    out = {}
+    spec = torch.randn(2, 1, 257, 33, 2, generator=g)
+    out["spec"] = spec
+    out["amplitude"] = Amplitude()(spec)
+
+    def first_input(model, x):
+        grabbed = {}
+
+        def hook(mod, inp):
+            if "x" not in grabbed:
+                grabbed["x"] = inp[0].detach().clone()
+        hs = [m.register_forward_pre_hook(hook) for m in model.modules() if len(list(m.children())) == 0]
+        model.eval()
+        try:
+            with torch.no_grad():
+                model(x)
+        except Exception as e:          # only the first layer's input matters
+            print("   (forward stopped after the first layer:", type(e).__name__, ")")
+        for h in hs:
+            h.remove()
+        return grabbed["x"]
+    out["power"] = first_input(UNet(unet_channels=1, unet_layer=4), spec).reshape(2, 1, 257, 33)
+    # dnn.py:98-111: sqrt -> squeeze -> transpose(1, 2) -> reshape(batch*frame, feature) is what the first Linear sees
+    out["magnitude"] = first_input(DeepNeuralNetwork(nfft=512, hidden_layer=32, dnn_ema=False), spec).reshape(2, 33, 257).transpose(1, 2).reshape(2, 1, 257, 33)
+    crn_spec = torch.randn(2, 1, 161, 20, 2, generator=g)
+    out["crn_spec"] = crn_spec
+    out["crn"] = first_input(CRN(use_lstm=False), crn_spec)
+    save("features", **out)
+
+
 if __name__ == "__main__":
+    if "--only-f-rows" in sys.argv:
+        gen_losses_evaluate_collate_features()
+        sys.exit(0)
+    gen_losses_evaluate_collate_features()
     gen_tasnet_and_metric()
     if "--only-new" in sys.argv:
         sys.exit(0)

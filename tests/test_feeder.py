@@ -37,3 +37,17 @@ def test_pinned_feeder_uploads_every_batch_unchanged():
         assert torch.equal(mix.cpu(), mix_ref) and torch.equal(src.cpu(), src_ref)
         seen += 1
     assert seen == 5 and f.bytes_per_batch > 0
+
+
+@pytest.mark.parametrize("tag,drop", [("drop", True), ("pad", False)])
+def test_collate_pad_matches_reference_run_golden(tag, drop):
+    """feeder.collate_pad against the output of the REAL reference's collate_fn_pad (src/distrib.py:38-98) on the
+    same clips: tests/golden/collate.npz, made by tests/golden/make_golden.py."""
+    import numpy as np
+    from conftest import golden
+    gd = golden("collate")
+    batch = [(torch.from_numpy(gd[f"mix_{i}"]), torch.from_numpy(gd[f"src_{i}"])) for i in range(4)]
+    mix, src, nsegs = feeder.collate_pad(batch, int(gd["segment_length"]), drop)
+    assert np.array_equal(mix.numpy(), gd[f"batch_mix_{tag}"])
+    assert np.array_equal(src.numpy(), gd[f"batch_src_{tag}"])
+    assert list(nsegs) == list(gd[f"index_{tag}"])

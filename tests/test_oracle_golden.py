@@ -146,3 +146,54 @@ def test_si_sdr_metric_oracle_matches_reference():
     g = golden("tasnet_metric")
     assert abs(oref.si_sdr_metric_ref(g["sdr_ref"], g["sdr_est"]) - float(g["sdr"])) < 1e-6
     assert abs(oref.si_sdr_metric_ref(g["sdr_ref"], 0.01 * g["sdr_est"] + 0.5) - float(g["sdr_scaled"])) < 1e-5
+
+
+# ---------------------------------------------------------------- SURVEY 8f rows, pinned to the REAL reference
+# (fixtures: tests/golden/make_golden.py::gen_losses_evaluate_collate_features imports src.loss, src.evaluate.evaluate,
+# src.distrib.collate_fn_pad and real model forwards).  These oracle functions are restatements of torch expressions,
+# so the bar is bit-exactness (same ops in the same order on the same CPU build).
+def test_si_snr_and_psa_oracles_are_bit_exact_with_reference_src_loss():
+    gd = golden("losses")
+    for tag in "abc":
+        s1, s2 = torch.from_numpy(gd[f"sisnr_s1_{tag}"]), torch.from_numpy(gd[f"sisnr_s2_{tag}"])
+        got = oref.si_snr_ref(s1, s2)
+        assert float(got) == float(gd[f"sisnr_{tag}"]), tag
+        assert float(-got) == float(gd[f"sisdr_loss_{tag}"]), tag
+    enh, tgt, mix = (torch.from_numpy(gd[k]) for k in ("psa_enh", "psa_tgt", "psa_mix"))
+    assert float(oref.psa_loss_ref(enh, tgt, mix)) == float(gd["psa"])
+
+
+@pytest.mark.parametrize("tag", ["zscore", "plain", "n1024"])
+def test_evaluate_oracle_is_bit_exact_with_reference_evaluate(tag):
+    import types
+    gd = golden("evaluate")
+    n_fft, hop, nfeat, zscore = (int(v) for v in gd[f"meta_{tag}"])
+    conf = types.SimpleNamespace(dset=types.SimpleNamespace(norm="z-score" if zscore else "none", sample_rate=16000),
+                                 model=types.SimpleNamespace(name="unet", n_fft=n_fft, hop_length=hop, win_length=n_fft, center=True,
+                                                             segment=nfeat / 16000.0))
+    got = oref.evaluate_ref(torch.from_numpy(gd[f"mix_{tag}"]), None, conf)
+    want = gd[f"enh_{tag}"]
+    assert got.shape == want.shape
+    assert np.array_equal(got.numpy(), want), rel(got.numpy(), want)
+    # model=None makes evaluate() a (z-score -> STFT -> iSTFT -> stitch -> de-normalise) identity up to fp32 round-off
+    assert rel(want, gd[f"mix_{tag}"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag,drop", [("drop", True), ("pad", False)])
+def test_collate_oracle_is_bit_exact_with_reference_collate_fn_pad(tag, drop):
+    gd = golden("collate")
+    batch = [(torch.from_numpy(gd[f"mix_{i}"]), torch.from_numpy(gd[f"src_{i}"])) for i in range(4)]
+    mix, src, index = oref.collate_fn_pad_ref(batch, int(gd["segment_length"]), drop_last=drop)
+    assert np.array_equal(mix.numpy(), gd[f"batch_mix_{tag}"])
+    assert np.array_equal(src.numpy(), gd[f"batch_src_{tag}"])
+    assert list(index) == list(gd[f"index_{tag}"])
+
+
+def test_magnitude_feature_oracle_is_bit_exact_with_reference_model_forwards():
+    gd = golden("features")
+    spec = torch.from_numpy(gd["spec"])
+    for kind in ("amplitude", "power", "magnitude"):
+        assert np.array_equal(oref.magnitude_feature_ref(spec, kind).numpy(), gd[kind]), kind
+    got = oref.magnitude_feature_ref(torch.from_numpy(gd["crn_spec"]), "crn").numpy()
+    assert np.array_equal(np.isnan(got), np.isnan(gd["crn"]))          # sqrt(re^2 - im^2): NaN where |im| > |re|, kept
+    assert np.array_equal(np.nan_to_num(got), np.nan_to_num(gd["crn"]))
