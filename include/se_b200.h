@@ -70,6 +70,24 @@ int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t ncli
                          int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft, int hop,
                          int win_length, float scale, void* stream);
 
+/* ---- evaluate()'s normalisation and stitch folded into the transforms (src/evaluate.py:18-21, 84-96).
+ * se_row_stats: x [rows, row_stride] (len valid samples) -> stats [rows,4] = (mean, 1/(std+1e-9), std+1e-9, 0) with
+ *   torch.mean / torch.std (unbiased) semantics, double accumulators.
+ * se_stft_segments_norm_fwd: se_stft_segments_fwd with the z-score (x - mean) / (std + 1e-9) applied to the valid samples
+ *   while they are staged (the zero-filled tail stays zero, like the reference's pad after normalisation).  Clip c reads
+ *   statistics row (c / stats_div) * stats_c + c % stats_c; stats == NULL: no normalisation.
+ * se_istft_stitch_fwd: spec [(nseg*nclip), F, T, 2] (row = s*nclip + c) -> out [nclip, out_stride]: istft_custom of every
+ *   segment, then `enhanced[..., :num_feature] = output[0]` and the last `stride` samples of each later segment appended
+ *   (:84-88), trimmed to out_len (:90) and de-normalised y * (std+1e-9) + mean (:92-93) -- in one launch that synthesises
+ *   only the frames overlapping the kept samples (stride/hop blocks + halo per later segment instead of all T frames). */
+int se_row_stats(const float* x, float* stats, int64_t rows, int64_t len, int64_t row_stride, void* stream);
+int se_stft_segments_norm_fwd(const float* x, float* spec, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
+                              int64_t nclip, int64_t clip_len, int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft,
+                              int hop, int win_length, float scale, void* stream);
+int se_istft_stitch_fwd(const float* spec, float* out, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
+                        int64_t nclip, int64_t nframe, int64_t num_feature, int64_t stride, int64_t out_len, int64_t out_stride,
+                        int n_fft, int hop, int win_length, float scale, void* stream);
+
 /* adjoint of se_stft_fwd (autograd of src/evaluate.py:109-120):
  * gspec [rows,F,T,2] (dL/dRe, dL/dIm) -> gx [rows,N]; accumulate != 0 adds into gx. */
 int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop,

@@ -81,6 +81,13 @@ static cudaError_t dispatch_synthesis(const SynArgs& a, int64_t rows, int n_fft,
     return e;
 }
 
+template <class G>
+static cudaError_t run_stitch(SynArgs a, StitchArgs s, cudaStream_t st) {
+    s.chunks0 = plan_synthesis(s.nclip, a.b_hi - a.b_lo, G::OLA, G::MINB, G::FR);
+    const unsigned grid = (unsigned)(s.nclip * s.chunks0 + (s.nseg - 1) * s.nclip);
+    return launch(k_synthesis_stitch<G>, grid, G::NT, Smem<G>::SYNTH_ISTFT, st, a, s);
+}
+
 extern "C" {
 
 int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
@@ -124,7 +131,22 @@ int se_magnitude_feature(const float* spec, float* feat, int64_t count, int kind
 
 int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t nclip, int64_t clip_len, int64_t clip_stride,
                          int64_t seg_stride, int64_t nsample, int n_fft, int hop, int win_length, float scale, void* stream) {
+    return se_stft_segments_norm_fwd(x, spec, nullptr, 1, 1, nseg, nclip, clip_len, clip_stride, seg_stride, nsample, n_fft, hop,
+                                     win_length, scale, stream);
+}
+
+int se_row_stats(const float* x, float* stats, int64_t rows, int64_t len, int64_t row_stride, void* stream) {
+    if (!x || !stats) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (rows <= 0 || len <= 0 || row_stride < len) return fail(SE_ERR_BAD_ARG, "need rows > 0, len > 0, row_stride >= len");
+    cudaError_t e = launch(k_row_stats, (unsigned)rows, 256u, 0, (cudaStream_t)stream, x, reinterpret_cast<float4*>(stats), len, row_stride);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_row_stats launch");
+}
+
+int se_stft_segments_norm_fwd(const float* x, float* spec, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
+                              int64_t nclip, int64_t clip_len, int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft,
+                              int hop, int win_length, float scale, void* stream) {
     if (!x || !spec) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (stats && (stats_div <= 0 || stats_c <= 0)) return fail(SE_ERR_BAD_ARG, "bad statistics indexing");
     if (nseg <= 0 || nclip <= 0 || clip_len <= 0 || seg_stride <= 0 || clip_stride < clip_len)
         return fail(SE_ERR_BAD_ARG, "bad segment geometry");
     const int64_t rows = nseg * nclip;
@@ -135,8 +157,11 @@ int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t ncli
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
     a.in = x; a.out = spec; a.in_stride = seg_stride; a.clip_stride = clip_stride; a.seg_rows = (int)nclip;
     a.clip_len = (int)clip_len; a.nsample = (int)nsample; a.in_len = (int)nsample;
+    a.norm = reinterpret_cast<const float4*>(stats); a.norm_div = (int)stats_div; a.norm_c = (int)stats_c;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
-    const cudaError_t e = dispatch_analysis<LOAD_REFLECT>(a, rows, n_fft, hop, (cudaStream_t)stream);
+    cudaError_t e;
+    if (stats) SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));   // scalar engine: it has the normalising fill
+    else e = dispatch_analysis<LOAD_REFLECT>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_segments_fwd launch");
 }
 
@@ -183,6 +208,34 @@ int se_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, in
     a.nsample = (int)(n_fft + hop * (nframe - 1)); a.nframe = (int)nframe; a.pad = 0; a.edge_scale = 0.5f;
     const cudaError_t e = dispatch_analysis<LOAD_ENV>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_istft_bwd launch");
+}
+
+int se_istft_stitch_fwd(const float* spec, float* out, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
+                        int64_t nclip, int64_t nframe, int64_t num_feature, int64_t stride, int64_t out_len, int64_t out_stride,
+                        int n_fft, int hop, int win_length, float scale, void* stream) {
+    if (!spec || !out) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (nseg <= 0 || nclip <= 0 || nframe <= 0 || num_feature <= 0 || stride <= 0 || stride > num_feature || out_len <= 0 || out_stride < out_len)
+        return fail(SE_ERR_BAD_ARG, "bad stitch geometry");
+    if (out_len > num_feature + stride * (nseg - 1)) return fail(SE_ERR_BAD_ARG, "out_len exceeds the stitched length");
+    if (stats && (stats_div <= 0 || stats_c <= 0)) return fail(SE_ERR_BAD_ARG, "bad statistics indexing");
+    if (int rc = check_common(nseg * nclip, num_feature, n_fft, hop, win_length)) return rc;
+    if (!envelope_ok(n_fft, hop, win_length, false, nframe, n_fft / 2, n_fft / 2 + num_feature, 1e-11))
+        return fail(SE_ERR_ENVELOPE, "window overlap add min < 1e-11 (torch.istft raises the same)");
+    SynArgs a{};
+    if (int rc = get_tables(n_fft, hop, win_length, false, scale / (float)n_fft, a.tb)) return rc;
+    a.in = spec; a.out = out; a.nsample = (int)(n_fft + hop * (nframe - 1)); a.out_len = (int)num_feature;
+    a.nframe = (int)nframe;
+    a.b_lo = (n_fft / 2) / hop; a.b_hi = (int)((n_fft / 2 + num_feature + hop - 1) / hop);
+    a.accumulate = 0; a.edge_scale = 1.0f;
+    StitchArgs s{};
+    s.nclip = (int)nclip; s.nseg = (int)nseg; s.stride = (int)stride; s.num_feature = (int)num_feature;
+    s.clip_len = (int)out_len; s.out_stride = out_stride;
+    s.tail_b_lo = (int)((n_fft / 2 + num_feature - stride) / hop); s.tail_b_hi = a.b_hi;
+    s.norm = reinterpret_cast<const float4*>(stats); s.norm_div = (int)stats_div; s.norm_c = (int)stats_c;
+    // a later segment's tail is ONE chunk: its blocks plus the OLA halo must fit the kernel's group walk (any count does)
+    cudaError_t e;
+    SE_DISPATCH_GEO(n_fft, hop, (e = run_stitch<G>(a, s, (cudaStream_t)stream)));
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_istft_stitch_fwd launch");
 }
 
 }  // extern "C"

@@ -41,6 +41,10 @@ struct AnaArgs {            // analysis: waveform-like -> spectrum
     float edge_scale;       // multiplies DC and Nyquist outputs
     float* feat;            // optional second output [rows, F, T]: magnitude feature of the spectrum (a6)
     int feat_kind;
+    // evaluate()'s z-score folded into the fill (src/evaluate.py:18-21): per clip (mean, 1/(std+1e-9), std+1e-9, 0);
+    // clip -> statistics row = (clip / norm_div) * norm_c + clip % norm_c.  nullptr: no normalisation.
+    const float4* norm;
+    int norm_div, norm_c;
 };
 
 struct SynArgs {            // synthesis: spectrum -> waveform-like
@@ -57,12 +61,13 @@ struct SynArgs {            // synthesis: spectrum -> waveform-like
 };
 
 // ------------------------------------------------------------------ padded-signal samplers
-__device__ __forceinline__ float sample_reflect(const float* __restrict__ x, int n_half, int N, int n_fft, int i, int nvalid) {
+__device__ __forceinline__ float sample_reflect(const float* __restrict__ x, int n_half, int N, int n_fft, int i, int nvalid,
+                                                float mean = 0.f, float inv = 1.f) {
     if (i < 0 || i >= N + n_fft) return 0.f;
     int j = i - n_half;
     j = j < 0 ? -j : j;
     j = j >= N ? 2 * (N - 1) - j : j;
-    return j < nvalid ? __ldg(x + j) : 0.f;      // nvalid < N: zero-filled tail of the last segments
+    return j < nvalid ? (__ldg(x + j) - mean) * inv : 0.f;      // nvalid < N: zero-filled tail of the last segments
 }
 
 template <class G>
@@ -84,7 +89,8 @@ __device__ __forceinline__ float inv_env_at(const Tables& tb, int T, int i) {
 // the load held 90 % of the long-scoreboard samples before this change).
 template <class G, int LMODE>
 __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const float* __restrict__ src,
-                                           int p0, const AnaArgs& a, int tid, int nvalid = 0x7fffffff) {
+                                           int p0, const AnaArgs& a, int tid, int nvalid = 0x7fffffff,
+                                           float nm_mean = 0.f, float nm_inv = 1.f) {
     constexpr int SLOTS = G::SROWS * G::HOP / 2;                 // float2 slots
     constexpr int K = (SLOTS + G::NT - 1) / G::NT;
     float2 v[K];
@@ -114,8 +120,8 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
             if (slot >= SLOTS) continue;
             const int i = p0 + 2 * slot;
             if (LMODE == LOAD_REFLECT) {
-                v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i, nvalid),
-                                   sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1, nvalid));
+                v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i, nvalid, nm_mean, nm_inv),
+                                   sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1, nvalid, nm_mean, nm_inv));
             } else if (LMODE == LOAD_ZEROPAD) {
                 const int j = i - a.pad;
                 v[k] = make_float2((j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f,
@@ -133,6 +139,7 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
         if (slot >= SLOTS) continue;
         const int rel = 2 * slot;
         float2 w = v[k];
+        if (LMODE == LOAD_REFLECT && interior) w = make_float2((w.x - nm_mean) * nm_inv, (w.y - nm_mean) * nm_inv);
         if (LMODE == LOAD_ENV) {      // gy / envelope (zero where the envelope is empty)
             const int i = p0 + rel;
             w.x *= inv_env_at<G>(a.tb, a.nframe, i);
@@ -488,10 +495,16 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
         const int64_t left = (int64_t)a.clip_len - (int64_t)seg * a.in_stride;
         nvalid = left < 0 ? 0 : (left < a.nsample ? (int)left : a.nsample);
     }
+    float nm_mean = 0.f, nm_inv = 1.f;
+    if (a.norm) {
+        const float4 st = __ldg(a.norm + (clip / a.norm_div) * a.norm_c + clip % a.norm_c);
+        nm_mean = st.x;
+        nm_inv = st.y;
+    }
     for (int g = 0; g < a.gpc; ++g) {
         const int f_base = (chunk * a.gpc + g) * G::FR;
         if (f_base >= a.nframe) break;
-        fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid, nvalid);
+        fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid, nvalid, nm_mean, nm_inv);
         __syncthreads();
         analysis_passes<G>(stage, tb, zb, unit, fr);
         const int t = f_base + fr;
@@ -547,6 +560,126 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis(const SynArgs a) {
     if (EMODE == EMIT_ADJ && c.last) {
         __syncthreads();
         finish_adj<G>(hold, out_row, a.nsample, a.accumulate, 1.0f, tid);
+    }
+}
+
+// ------------------------------------------------------------------ evaluate(): iSTFT + stitch + de-normalise
+// src/evaluate.py:72-96: every segment is inverse-transformed, then only segment 0 (whole) and the LAST `stride` samples
+// of each later segment are kept and the z-score is undone.  Here one launch writes the stitched clip directly: CTAs
+// of segment 0 run the usual chunked synthesis, one CTA per later segment synthesises only the frames that overlap its
+// kept tail (stride / hop blocks + the OLA halo instead of all T frames), and the emitter applies
+// y * (std + 1e-9) + mean and the final trim to the clip length.
+struct StitchArgs {
+    int nclip, nseg;            // rows of the spectrum = nseg * nclip, row = seg * nclip + clip
+    int chunks0;                // chunks per segment-0 row
+    int stride, num_feature;    // kept tail length, segment length
+    int clip_len;               // samples written per clip (the mixture's length)
+    int64_t out_stride;         // floats between clips of the output
+    int tail_b_lo, tail_b_hi;   // block range of a later segment's kept tail
+    const float4* norm;         // per-clip (mean, 1/scale, scale, 0) or nullptr
+    int norm_div, norm_c;
+};
+
+template <class G>
+__device__ __forceinline__ void emit_istft_stitch(const float* __restrict__ ostage, float* __restrict__ clip_out, int f_base,
+                                                  const Chunk& c, const SynArgs& a, const StitchArgs& s, int seg,
+                                                  float scale, float mean, int tid) {
+    const int keep_lo = seg == 0 ? 0 : s.num_feature - s.stride;
+    const int shift = seg == 0 ? 0 : s.num_feature + s.stride * (seg - 1) - keep_lo;     // segment sample -> clip position
+    for (int idx = tid; idx < G::FR * G::HOP; idx += G::NT) {
+        const int blk = idx / G::HOP, o = idx - blk * G::HOP;
+        const int b = f_base + blk;
+        if (b < c.b0 || b >= c.b1) continue;
+        const int i = b * G::HOP + o, sl = i - G::N / 2;                                // segment-local sample
+        if (sl < keep_lo || sl >= s.num_feature) continue;
+        const int pos = sl + shift;
+        if (pos >= s.clip_len) continue;
+        float r = 0.f;
+        if (i < a.nsample) r = ostage[blk * G::SROW + o] * inv_env_at<G>(a.tb, a.nframe, i);
+        clip_out[pos] = r * scale + mean;
+    }
+}
+
+template <class G>
+__global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis_stitch(const SynArgs a, const StitchArgs s) {
+    SE_SMEM_DECL;
+    float2* zb = reinterpret_cast<float2*>(se_smem);
+    float* ostage = reinterpret_cast<float*>(se_smem + Smem<G>::ZB);
+    const int tid = threadIdx.x, fr = tid % G::FR, unit = tid / G::FR;
+    pdl_launch_dependents();
+    const Tables tb = stage_tables<G>(a.tb, se_smem + Smem<G>::ZB + Smem<G>::OSTAGE, tid);
+    __syncthreads();
+    pdl_wait();
+    int seg, clip;
+    Chunk c;
+    const int head = s.nclip * s.chunks0;
+    if ((int)blockIdx.x < head) {
+        seg = 0;
+        clip = blockIdx.x / s.chunks0;
+        c = make_chunk<G>(blockIdx.x - clip * s.chunks0, s.chunks0, a.b_lo, a.b_hi);
+    } else {
+        const int idx = blockIdx.x - head;
+        seg = 1 + idx / s.nclip;
+        clip = idx - (seg - 1) * s.nclip;
+        c = make_chunk<G>(0, 1, s.tail_b_lo, s.tail_b_hi);
+    }
+    float scale = 1.f, mean = 0.f;
+    if (s.norm) {
+        const float4 st = __ldg(s.norm + (clip / s.norm_div) * s.norm_c + clip % s.norm_c);
+        mean = st.x;
+        scale = st.z;
+    }
+    const float2* spec = reinterpret_cast<const float2*>(a.in) + ((size_t)seg * s.nclip + clip) * G::F * a.nframe;
+    float* clip_out = a.out + (size_t)clip * s.out_stride;
+    float2 carry[G::TA][G::SEG];
+#pragma unroll
+    for (int i = 0; i < G::TA; ++i)
+#pragma unroll
+        for (int q = 0; q < G::SEG; ++q) carry[i][q] = make_float2(0.f, 0.f);
+    for (int g = 0; g < c.ngroups; ++g) {
+        const int f_base = c.f0 + g * G::FR;
+        const int t = f_base + fr;
+        SE_TC_PRAGMA
+        for (int i = 0; i < G::TC; ++i) {
+            const int p = unit + i * G::NU;
+            float2 ya[8], yb[8], nyq;
+            load_task_ft2<G>(spec, a.nframe, t, p, ya, yb, nyq, a.edge_scale);
+            synthesis_task<G>(zb, tb, p, fr, ya, yb, nyq);
+        }
+        synthesis_tail<G>(zb, tb, ostage, unit, fr, carry);
+        emit_istft_stitch<G>(ostage, clip_out, f_base, c, a, s, seg, scale, mean, tid);
+    }
+}
+
+// per-row mean and unbiased standard deviation (torch.mean / torch.std, src/evaluate.py:19-20), double accumulators:
+// stats[row] = (mean, 1 / (std + 1e-9), std + 1e-9, 0)
+static __global__ void __launch_bounds__(256) k_row_stats(const float* __restrict__ x, float4* __restrict__ stats, int64_t len,
+                                                  int64_t row_stride) {
+    __shared__ double sh[2][8];
+    pdl_launch_dependents();
+    pdl_wait();
+    const float* row = x + (size_t)blockIdx.x * row_stride;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t i = threadIdx.x; i < len; i += 256) {
+        const double v = (double)__ldg(row + i);
+        s1 += v;
+        s2 += v * v;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        const double mean = a / (double)len;
+        double var = len > 1 ? (b - (double)len * mean * mean) / (double)(len - 1) : 0.0;
+        var = var > 0.0 ? var : 0.0;
+        const double scale = sqrt(var) + 1e-9;
+        stats[blockIdx.x] = make_float4((float)mean, (float)(1.0 / scale), (float)scale, 0.f);
     }
 }
 

@@ -75,10 +75,26 @@ MONARCH_SPEECH_SEPARTAION_MODELS = ("mel-rnn", "dcunet", "crn", "dnn", "unet", "
 STFT_MODELS = ("mel-rnn", "dcunet", "crn", "dnn", "unet", "rnn-stft-mask")           # src/model/types.py:5
 
 
-def segment_stft(wave, num_feature, stride, config):
+def row_stats(wave):
+    """Per-(batch, channel) mean and unbiased std of [B,C,L] in one launch: [B*C, 4] = (mean, 1/(std+1e-9), std+1e-9, 0)
+    -- the z-score of src/evaluate.py:18-21, consumed by `segment_stft` / `istft_stitch` instead of being applied as
+    separate elementwise passes."""
+    import torch
+    from . import _native as nv
+    x = ops._as_f32(wave).contiguous()
+    nv.require_cuda_f32(x)
+    rows, length = x.shape[0] * x.shape[1], x.shape[2]
+    stats = torch.empty((rows, 4), dtype=torch.float32, device=x.device)
+    with nv.on_device(x.device):
+        nv.check(nv.lib().se_row_stats(x.data_ptr(), stats.data_ptr(), rows, length, length, nv.stream_ptr(x.device)))
+    return stats
+
+
+def segment_stft(wave, num_feature, stride, config, stats=None):
     """`_prepare_input_wav_zero_filled` (src/evaluate.py:164-183) + reshape (:35-36) + `stft_custom` (:39)
     in one launch: the overlapping segments are never materialised (they are strided views of the clip;
-    the zero-filled tail is synthesised in the kernel).  wave [B,C,L] -> [nseg*B, C, F, T, 2]."""
+    the zero-filled tail is synthesised in the kernel).  wave [B,C,L] -> [nseg*B, C, F, T, 2].
+    stats (from `row_stats`): the z-score is applied to the samples while they are staged."""
     import torch
     from . import _native as nv
     n_fft, hop, win = _cfg(config)
@@ -92,18 +108,45 @@ def segment_stft(wave, num_feature, stride, config):
     padded = length + (stride - rem if rem else 0)
     nseg = (padded - num_feature) // stride + 1
     x = ops._as_f32(wave).contiguous()
-    nv.require_cuda_f32(x)
+    nv.require_cuda_f32(x, stats)
     nf, nt = n_fft // 2 + 1, 1 + num_feature // hop
     out = torch.empty((nseg * nb, nc, nf, nt, 2), dtype=torch.float32, device=x.device)
     with nv.on_device(x.device):
-        nv.check(nv.lib().se_stft_segments_fwd(x.data_ptr(), out.data_ptr(), nseg, nb * nc, length, length, stride,
-                                               num_feature, n_fft, hop, win, 1.0 / win, nv.stream_ptr(x.device)))
+        nv.check(nv.lib().se_stft_segments_norm_fwd(x.data_ptr(), out.data_ptr(), 0 if stats is None else stats.data_ptr(),
+                                                    nb * nc, nb * nc, nseg, nb * nc, length, length, stride, num_feature, n_fft, hop,
+                                                    win, 1.0 / win, nv.stream_ptr(x.device)))
     return out, nseg
 
 
+def istft_stitch(spec, nseg, num_feature, stride, out_len, config, stats=None, stats_channels=1):
+    """istft_custom of every segment + the reference's stitch (src/evaluate.py:84-90: segment 0 whole, then the last `stride`
+    samples of each later segment, trimmed to out_len) + de-normalisation (:92-93) in ONE launch that only synthesises the
+    frames overlapping kept samples.  spec [nseg*K, ..., F, T, 2] (segment-major rows) -> [K*..., out_len].
+    stats: `row_stats` of the [B,C,L] mixture; stats_channels = C (a sources dimension between B and C shares them)."""
+    import torch
+    from . import _native as nv
+    n_fft, hop, win = _cfg(config)
+    ops._check_cfg(n_fft, hop, win)
+    s = ops._as_f32(spec).contiguous()
+    nv.require_cuda_f32(s, stats)
+    nf, nt = s.shape[-3], s.shape[-2]
+    rows = s.numel() // (nf * nt * 2)
+    if s.shape[-1] != 2 or nf != n_fft // 2 + 1 or rows % nseg:
+        raise RuntimeError(f"istft_stitch: expected [nseg*K, ..., {n_fft // 2 + 1}, T, 2] with nseg = {nseg}, got {tuple(spec.shape)}")
+    nclip = rows // nseg
+    out = torch.empty((nclip, out_len), dtype=torch.float32, device=s.device)
+    div = 1 if stats is None else max(nclip * stats_channels // stats.shape[0], 1)      # = nsrc * C
+    with nv.on_device(s.device):
+        nv.check(nv.lib().se_istft_stitch_fwd(s.data_ptr(), out.data_ptr(), 0 if stats is None else stats.data_ptr(), div,
+                                              stats_channels, nseg, nclip, nt, num_feature, stride, out_len, out_len, n_fft, hop,
+                                              win, float(win), nv.stream_ptr(s.device)))
+    return out
+
+
 def stitch_segments(output, num_feature, stride, out_len):
-    """src/evaluate.py:84-90 without the Python loop: the first segment whole, then the last `stride`
-    samples of every later segment.  output [nseg, ..., num_feature] -> [..., out_len]."""
+    """src/evaluate.py:84-90 without the Python loop (waveform models; the STFT models stitch inside `istft_stitch`):
+    the first segment whole, then the last `stride` samples of every later segment.  output [nseg, ..., num_feature]
+    -> [..., out_len]."""
     import torch
     nseg = output.shape[0]
     head = output[0]
@@ -118,43 +161,59 @@ def evaluate(mixture, model, device, config):
     """Drop-in for `evaluate(mixture, model, device, config)` (src/evaluate.py:10-98): normalise,
     cut into `config.model.segment`-second segments with stride win_length, STFT, model, iSTFT,
     stitch, de-normalise.  Everything runs on `device` (the reference runs the STFT on the CPU tensor
-    and moves to the device afterwards, :39,50)."""
+    and moves to the device afterwards, :39,50).
+
+    STFT models: three launches around the model -- `row_stats`, `segment_stft` (z-score folded into the staging of the
+    strided segment views) and `istft_stitch` (inverse transform of only the frames the stitch keeps, de-normalised and
+    written straight into the stitched clip).  The result comes back on `mixture`'s device (the reference builds it with
+    torch.zeros on the CPU, :83; its test loop feeds CPU mixtures, src/solver.py:584)."""
     import torch
     with torch.no_grad():
         x = mixture.to(device)
         norm = getattr(config.dset, "norm", None)
-        if norm == "z-score":
-            mean = torch.mean(x, dim=-1, keepdim=True)
-            std = torch.std(x, dim=-1, keepdim=True)
-            x = (x - mean) / (std + 1e-9)
-        elif norm == "linear-scale":
+        if norm == "linear-scale":
             # the reference indexes the (values, indices) tuple of torch.max here and fails (:23-25)
             raise NotImplementedError("dset.norm='linear-scale' is broken in the reference (src/evaluate.py:23-25)")
         stride = config.model.win_length
         num_feature = int(config.dset.sample_rate * config.model.segment)
         nbatch, nchannel, length = x.shape
         name = config.model.name
+        multi = bool(model) and name in MULTI_SPEECH_SEPERATION_MODELS
         if name in STFT_MODELS:
-            batch, nseg = segment_stft(x, num_feature, stride, config.model)
-        else:
-            rem = (length - num_feature) % stride
-            xp = torch.nn.functional.pad(x, [0, stride - rem]) if rem else x
-            batch = xp.unfold(-1, num_feature, stride).movedim(-2, 0)             # [nseg,B,C,N] view
-            nseg = batch.shape[0]
-            batch = batch.reshape(nseg * nbatch, nchannel, num_feature)
+            stats = row_stats(x) if norm == "z-score" else None
+            batch, nseg = segment_stft(x, num_feature, stride, config.model, stats)
+            if model:
+                model.eval()
+                half = int(batch.shape[0] // 2)                                  # :48-56 two half-batches
+                output = torch.cat([model(batch[:half]), model(batch[half:])], dim=0)
+            else:
+                output = batch
+            enhanced = istft_stitch(output, nseg, num_feature, stride, length, config.model, stats, nchannel)
+            if multi:
+                enhanced = enhanced.reshape(nbatch, len(config.model.sources), nchannel, length)
+            else:
+                enhanced = enhanced.reshape(nbatch, nchannel, length)
+            return enhanced.to(mixture.device)
+        # waveform models: no transform on the path -- normalise, view the segments, model, stitch
+        if norm == "z-score":
+            mean = torch.mean(x, dim=-1, keepdim=True)
+            std = torch.std(x, dim=-1, keepdim=True)
+            x = (x - mean) / (std + 1e-9)
+        rem = (length - num_feature) % stride
+        xp = torch.nn.functional.pad(x, [0, stride - rem]) if rem else x
+        batch = xp.unfold(-1, num_feature, stride).movedim(-2, 0)             # [nseg,B,C,N] view
+        nseg = batch.shape[0]
+        batch = batch.reshape(nseg * nbatch, nchannel, num_feature)
         if model:
             model.eval()
-            half = int(batch.shape[0] // 2)                                      # :48-56 two half-batches
+            half = int(batch.shape[0] // 2)
             output = torch.cat([model(batch[:half]), model(batch[half:])], dim=0)
         else:
             output = batch
         if name in MONARCH_SPEECH_SEPARTAION_MODELS:
             output = torch.unsqueeze(output, dim=1)
-        if name in STFT_MODELS:
-            output = istft_custom(output, num_feature, config.model)
-        if model and name in MULTI_SPEECH_SEPERATION_MODELS:
-            nsrc = len(config.model.sources)
-            output = output.reshape(nseg, nbatch, nsrc, nchannel, num_feature)
+        if multi:
+            output = output.reshape(nseg, nbatch, len(config.model.sources), nchannel, num_feature)
         else:
             output = output.reshape(nseg, nbatch, nchannel, num_feature)
         enhanced = stitch_segments(output, num_feature, stride, length)
@@ -162,4 +221,4 @@ def evaluate(mixture, model, device, config):
             if enhanced.dim() == mean.dim() + 1:
                 mean, std = mean.unsqueeze(1), std.unsqueeze(1)
             enhanced = enhanced * (std + 1e-9) + mean
-    return enhanced
+    return enhanced.to(mixture.device)

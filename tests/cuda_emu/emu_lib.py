@@ -236,6 +236,32 @@ def stft_segments_fwd(x, nseg, seg_stride, nsample, n, hop, win, scale):
     return out
 
 
+def row_stats(x):
+    rows, length = x.shape
+    out = np.full((rows, 4), np.nan, np.float32)
+    check(lib().se_row_stats(ptr(x), ptr(out), i64(rows), i64(length), i64(length), None))
+    return out
+
+
+def stft_segments_norm_fwd(x, stats, nseg, seg_stride, nsample, n, hop, win, scale):
+    nclip, clip_len = x.shape
+    T = 1 + nsample // hop
+    out = np.full((nseg * nclip, n // 2 + 1, T, 2), np.nan, np.float32)
+    check(lib().se_stft_segments_norm_fwd(ptr(x), ptr(out), ptr(stats) if stats is not None else None, i64(nclip), i64(nclip),
+                                          i64(nseg), i64(nclip), i64(clip_len), i64(clip_len), i64(seg_stride), i64(nsample),
+                                          ci(n), ci(hop), ci(win), f32(scale), None))
+    return out
+
+
+def istft_stitch_fwd(spec, stats, nseg, nclip, nfeat, stride, out_len, n, hop, win, scale, div=None, chan=None):
+    T = spec.shape[-2]
+    out = np.full((nclip, out_len), np.nan, np.float32)
+    check(lib().se_istft_stitch_fwd(ptr(spec), ptr(out), ptr(stats) if stats is not None else None, i64(div or nclip), i64(chan or nclip),
+                                    i64(nseg), i64(nclip), i64(T), i64(nfeat), i64(stride), i64(out_len), i64(out_len),
+                                    ci(n), ci(hop), ci(win), f32(scale), None))
+    return out
+
+
 def spectral_loss(enh, target, n, hop, win, kind, gout=1.0):
     rows, N = target.shape
     lib().se_spectral_loss_workspace_bytes.restype = ctypes.c_int64

@@ -431,3 +431,37 @@ def test_emu_pair_engine_loss_odd_rows_ragged_and_carry(rows, N, groups, monkeyp
         out[eng] = (sums.copy(), g.copy())
     assert rel(out["2"][0], out["1"][0]) < 1e-5
     assert rel(out["2"][1], out["1"][1]) < 1e-3      # both sit within 1e-3 of float64; the gradient is ill-conditioned
+
+
+@pytest.mark.parametrize("tag", ["zscore", "plain", "n1024"])
+def test_emu_evaluate_fused_stats_segments_stitch_match_reference_golden(tag):
+    """evaluate(model=None) as three launches -- row statistics, segment STFT with the z-score folded into the fill,
+    iSTFT that synthesises only the kept frames and writes the stitched, de-normalised clip -- against the output of the
+    REAL reference's evaluate() (tests/golden/evaluate.npz) and, with a toy spectral mask between the two transforms,
+    against the oracle restatement of the same flow."""
+    gd = golden("evaluate")
+    n_fft, hop, nfeat, zscore = (int(v) for v in gd[f"meta_{tag}"])
+    mix = gd[f"mix_{tag}"]
+    nb, nc, length = mix.shape
+    wav = np.ascontiguousarray(mix.reshape(nb * nc, length))
+    stride = n_fft
+    rem = (length - nfeat) % stride
+    nseg = (length + (stride - rem if rem else 0) - nfeat) // stride + 1
+    stats = E.row_stats(wav) if zscore else None
+    if zscore:
+        t = torch.from_numpy(wav)
+        assert rel(stats[:, 0], t.mean(-1).numpy()) < 1e-5 and rel(stats[:, 2], (t.std(-1) + 1e-9).numpy()) < 1e-6
+    spec = E.stft_segments_norm_fwd(wav, stats, nseg, stride, nfeat, n_fft, hop, n_fft, 1.0 / n_fft)
+    assert not np.isnan(spec).any()
+    out = E.istft_stitch_fwd(spec, stats, nseg, nb * nc, nfeat, stride, length, n_fft, hop, n_fft, float(n_fft))
+    assert not np.isnan(out).any()
+    assert rel(out.reshape(mix.shape), gd[f"enh_{tag}"]) < 1e-5
+    # a "model" between the transforms: fixed smooth real mask over frequency
+    import types
+    f = np.linspace(0.2, 1.0, n_fft // 2 + 1, dtype=np.float32)[:, None, None]
+    out2 = E.istft_stitch_fwd(np.ascontiguousarray(spec * f), stats, nseg, nb * nc, nfeat, stride, length, n_fft, hop, n_fft, float(n_fft))
+    conf = types.SimpleNamespace(dset=types.SimpleNamespace(norm="z-score" if zscore else "none", sample_rate=16000),
+                                 model=types.SimpleNamespace(name="dnn", n_fft=n_fft, hop_length=hop, win_length=n_fft, center=True,
+                                                             segment=nfeat / 16000.0))
+    want = oref.evaluate_ref(torch.from_numpy(mix), lambda s: s * torch.from_numpy(f), conf).numpy()
+    assert rel(out2.reshape(mix.shape), want) < 1e-5
