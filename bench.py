@@ -477,7 +477,7 @@ def run_ours(args):
     gY = torch.empty_like(X)
     graw = torch.empty_like(X)
     ws = torch.empty(max(int(L.se_mrstft_workspace_bytes(rows, N)), 8), dtype=torch.uint8, device=dev)
-    sums = torch.empty(9, dtype=torch.float64, device=dev)
+    sums = torch.empty(9, dtype=torch.float64, device=dev)      # raw C-ABI step: equal shards, host-known global row count
     loss = torch.empty((), device=dev)
     one = torch.ones((), device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
@@ -568,15 +568,15 @@ def run_ours(args):
                 xr = torch.randn(rows, N, generator=gr)
                 allx.append(xr)
                 allc.append(xr + 0.3 * torch.randn(rows, N, generator=gr))
-            e1 = torch.cat(allx).reshape(rows * world, 1, N).to(dev).requires_grad_(True)
-            l_1 = se.loss_mrstft(e1, torch.cat(allc).reshape(rows * world, 1, N).to(dev))
-            (g_1,) = torch.autograd.grad(l_1, e1)
+            est_all = torch.cat(allx).reshape(rows * world, 1, N).to(dev).requires_grad_(True)
+            l_1 = se.loss_mrstft(est_all, torch.cat(allc).reshape(rows * world, 1, N).to(dev))
+            (g_1,) = torch.autograd.grad(l_1, est_all)
             gd = float((g_sh - g_1[:rows]).abs().max() / g_1[:rows].abs().max())
             shard_check = {"loss_sharded": float(l_sh), "loss_single_gpu": float(l_1),
                            "rel_diff": abs(float(l_sh) - float(l_1)) / abs(float(l_1)), "grad_rel_diff_rank0_rows": gd,
                            "what": f"loss_mrstft over {world} ranks x {rows} rows vs one GPU on all {rows * world} rows, same inputs"}
             assert shard_check["rel_diff"] < 1e-6 and gd < 1e-5, shard_check
-            del e1, g_1, allx, allc
+            del est_all, g_1, allx, allc
         del est, g_sh
         torch.cuda.empty_cache()
         sync_all()

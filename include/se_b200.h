@@ -141,6 +141,11 @@ int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample);
 int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums,
                        void* workspace, void* stream);
 int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsample, float* loss, void* stream);
+/* Uneven shards (ranks holding different row counts): keep the count on the device instead of guessing it on the host.
+ * sums10 = the 9 sums + [9] the row count; each rank stores its own count there before the exchange (all-reduce or
+ * se_mrstft_exchange_rows_value), which leaves the GLOBAL count in [9].  se_mrstft_loss_value_dev reads it from there;
+ * se_mrstft_loss_bwd does too when called with global_rows == 0 (its `sums` must then hold the 10 doubles). */
+int se_mrstft_loss_value_dev(const double* sums10, int64_t nsample, float* loss, void* stream);
 int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* sums, const float* gout,
                        int64_t global_rows, int64_t rows, int64_t nsample, float* g_est, void* stream);
 
@@ -153,14 +158,18 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
  * sums into every peer's buffer, waits (on the device) until all ranks' sums have arrived, adds them in
  * rank order -- every rank gets the same bits -- and writes the global sums in place and, if loss !=
  * NULL, the loss.  bufs is a HOST array of `world` device pointers, bufs[rank] the local buffer.
- * Every rank of the group must make the call the same number of times; a peer that does not show up
- * within ~60 s traps the kernel (the stream reports a CUDA error) instead of hanging. */
+ * Every rank of the group must make the call the same number of times.  A peer that does not show up within
+ * SE_P2P_SPIN_SECONDS (environment, read once; default 600, 0 = wait forever like NCCL would) does not hang the
+ * stream and does not kill the CUDA context: the kernel reports on stdout and poisons sums and loss with NaN.
+ * se_mrstft_exchange_rows_value is the same step on 10 doubles (sums10[9] = row count in, global row count out). */
 int se_p2p_create(void** local, unsigned char* handle64);
 int se_p2p_open(const unsigned char* handle64, void** peer);
 int se_p2p_close(void* peer);
 int se_p2p_destroy(void* local);
 int se_mrstft_exchange_value(double* sums, void* const* bufs, int world, int rank, int64_t global_rows,
                              int64_t nsample, float* loss, void* stream);
+int se_mrstft_exchange_rows_value(double* sums10, void* const* bufs, int world, int rank, int64_t nsample, float* loss,
+                                  void* stream);
 
 /* ---- STFT-domain training losses against a WAVEFORM target: what
  * loss_function(enhanced, stft_custom(sources)) computes with torch's mse_loss / l1_loss on

@@ -30,6 +30,7 @@ EXPORTS = (
     "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
     "se_mask_planar_fwd", "se_mask_planar_bwd", "se_conv_mask_istft_fwd", "se_conv_mask_istft_bwd",
     "se_p2p_create", "se_p2p_open", "se_p2p_close", "se_p2p_destroy", "se_mrstft_exchange_value",
+    "se_mrstft_exchange_rows_value", "se_mrstft_loss_value_dev",
 )
 
 MASK_MODES = {"real": 0, "E": 1, "C": 2, "R": 3}
@@ -183,6 +184,8 @@ def lib():
             L.se_p2p_close.argtypes = [_PTR]
             L.se_p2p_destroy.argtypes = [_PTR]
             L.se_mrstft_exchange_value.argtypes = [_PTR, _c.POINTER(_PTR), _INT, _INT, _I64, _I64, _PTR, _PTR]
+            L.se_mrstft_exchange_rows_value.argtypes = [_PTR, _c.POINTER(_PTR), _INT, _INT, _I64, _PTR, _PTR]
+            L.se_mrstft_loss_value_dev.argtypes = [_PTR, _I64, _PTR, _PTR]
             _lib = L
     return _lib
 

@@ -155,14 +155,24 @@ int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsampl
     double cnt[3];
     for (int r = 0; r < 3; ++r)
         cnt[r] = (double)global_rows * (kRes[r][0] / 2 + 1) * (double)(1 + nsample / kRes[r][1]);
-    cudaError_t e = launch(k_loss_value, 1u, 32u, 0, (cudaStream_t)stream, sums, cnt[0], cnt[1], cnt[2], loss);
+    cudaError_t e = launch(k_loss_value, 1u, 32u, 0, (cudaStream_t)stream, sums, cnt[0], cnt[1], cnt[2], loss, (const double*)nullptr);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_value launch");
+}
+
+int se_mrstft_loss_value_dev(const double* sums10, int64_t nsample, float* loss, void* stream) {
+    if (!sums10 || !loss) return fail(SE_ERR_BAD_ARG, "null pointer");
+    double per_row[3];
+    for (int r = 0; r < 3; ++r) per_row[r] = (double)(kRes[r][0] / 2 + 1) * (double)(1 + nsample / kRes[r][1]);
+    cudaError_t e = launch(k_loss_value, 1u, 32u, 0, (cudaStream_t)stream, sums10, per_row[0], per_row[1], per_row[2], loss, sums10 + 9);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_value_dev launch");
 }
 
 int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* sums, const float* gout, int64_t global_rows,
                        int64_t rows, int64_t nsample, float* g_est, void* stream) {
     if (!est || !workspace || !sums || !gout || !g_est) return fail(SE_ERR_BAD_ARG, "null pointer");
-    if (rows <= 0 || global_rows < rows || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need 0 < rows <= global_rows, nsample >= 2048");
+    // global_rows == 0: `sums` holds 10 doubles and sums[9] is the global row count (device side, uneven shards)
+    if (rows <= 0 || (global_rows != 0 && global_rows < rows) || nsample < 2048)
+        return fail(SE_ERR_BAD_ARG, "need 0 < rows <= global_rows (or global_rows == 0: count in sums[9]), nsample >= 2048");
     const float* refmag0 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + loss_partials_bytes(rows, nsample));
     for (int r = 0; r < 3; ++r)
         if (int rc = check_common(rows, nsample, kRes[r][0], kRes[r][1], kRes[r][2])) return rc;
@@ -181,7 +191,9 @@ int se_mrstft_loss_bwd(const float* est, const void* workspace, const double* su
         a.b_lo = 0; a.b_hi = (int)((nsample + n + hop - 1) / hop);
         a.accumulate = idx != 0;
         a.chained = idx != 0;
-        a.inv_count = (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe));
+        a.inv_count = global_rows ? (float)(1.0 / ((double)global_rows * (n / 2 + 1) * (double)a.nframe)) : 0.f;
+        a.rows_dev = global_rows ? nullptr : sums + 9;
+        a.bins_per_row = (double)(n / 2 + 1) * (double)a.nframe;
         a.inv_res = 1.0f / 3.0f;
         cudaError_t e;
         if (loss_recompute() && engine_version() == 2) {

@@ -701,6 +701,8 @@ struct LossArgs {
     int chained;             // fwd: 1 = independent follower of the previous loss-fwd kernel (see k_loss_fwd)
     float inv_count;         // 1 / (global_rows * F * T)
     float inv_res;           // 1 / number of resolutions
+    const double* rows_dev;  // bwd, optional: global row count on the device (uneven shards); overrides inv_count
+    double bins_per_row;     // F * T of this resolution
 };
 #define SE_MRSTFT_CLAMP 1e-7f
 
@@ -816,7 +818,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd(const LossArgs a) {
     const double d2 = a.sums[0], b2 = a.sums[1];
     const float gs = __ldg(a.gout) * a.inv_res;
     const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
-    const float beta = gs * a.inv_count;
+    const float beta = gs * (a.rows_dev ? (float)(1.0 / (a.rows_dev[0] * a.bins_per_row)) : a.inv_count);
     float* gx_row = a.g_est + (size_t)row * a.nsample;
     // n = 2048 runs single-group chunks (no OLA carry to keep live in its tighter register budget);
     // the smaller sizes carry the OLA tail across 2+ groups and recompute less halo
@@ -924,7 +926,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd_saved(const LossArg
     const double d2 = a.sums[0], b2 = a.sums[1];
     const float gs = __ldg(a.gout) * a.inv_res;
     const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
-    const float beta = gs * a.inv_count;
+    const float beta = gs * (a.rows_dev ? (float)(1.0 / (a.rows_dev[0] * a.bins_per_row)) : a.inv_count);
     float* gx_row = a.g_est + (size_t)row * a.nsample;
     const size_t rbase = (size_t)row * G::F * a.nframe;
     const size_t step = (size_t)G::S * a.nframe;
@@ -1010,11 +1012,14 @@ static __global__ void k_reduce_partials(const double* __restrict__ partials, in
     if (tid < 3) sums[3 * r + tid] = sh[tid][0];
 }
 
-static __global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss) {
+// c0..c2: global bins per resolution; rows_dev != nullptr: they are bins PER ROW and the global row count is read there
+static __global__ void k_loss_value(const double* __restrict__ sums, double c0, double c1, double c2, float* __restrict__ loss,
+                                    const double* __restrict__ rows_dev) {
     pdl_launch_dependents();
     pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const double cnt[3] = {c0, c1, c2};
+        const double rows = rows_dev ? rows_dev[0] : 1.0;
+        const double cnt[3] = {c0 * rows, c1 * rows, c2 * rows};
         double total = 0.0;
         for (int r = 0; r < 3; ++r) {
             const double d2 = sums[3 * r], b2 = sums[3 * r + 1], lm = sums[3 * r + 2];

@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd2(const LossArgs a, 
     const double d2 = a.sums[0], b2 = a.sums[1];
     const float gs = __ldg(a.gout) * a.inv_res;
     const float alpha = (d2 > 0.0 && b2 > 0.0) ? gs * (float)(1.0 / (sqrt(d2) * sqrt(b2))) : 0.f;
-    const float beta = gs * a.inv_count;
+    const float beta = gs * (a.rows_dev ? (float)(1.0 / (a.rows_dev[0] * a.bins_per_row)) : a.inv_count);
     const float* e0 = a.est + (size_t)r0 * a.nsample;
     const float* e1 = a.est + (size_t)r1 * a.nsample;
     float* g0 = a.g_est + (size_t)r0 * a.nsample;

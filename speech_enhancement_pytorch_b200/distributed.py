@@ -25,10 +25,11 @@ def shard_rows(n_utterances: int, world: int, rank: int) -> slice:
 
 
 def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place SUM all-reduce of the [9] float64 partial sums (NCCL on GPU, gloo in CPU tests)."""
+    """In-place SUM all-reduce of the [9] float64 partial sums, or of [10] = the sums + this rank's row count (the
+    exchange then leaves the global row count in [9]: uneven shards).  NCCL on GPU, gloo in CPU tests."""
     import torch.distributed as dist
-    if sums.dtype != torch.float64 or sums.numel() != 9:
-        raise ValueError("expected the 9 float64 MR-STFT partial sums")
+    if sums.dtype != torch.float64 or sums.numel() not in (9, 10):
+        raise ValueError("expected the 9 (or 9 + row count) float64 MR-STFT partial sums")
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return sums
 
@@ -83,12 +84,17 @@ class PeerExchange:
             raise
         self.ptrs = ptrs
 
-    def exchange_value(self, sums: torch.Tensor, global_rows: int, nsample: int, loss, stream: int):
+    def exchange_value(self, sums: torch.Tensor, global_rows, nsample: int, loss, stream: int):
+        """sums [9] with a host-known global_rows, or sums [10] (global_rows None): [9] carries this rank's row count
+        in and the global count out, so uneven shards need no guess."""
         from . import _native as nv
-        if sums.dtype != torch.float64 or sums.numel() != 9 or sums.device != self.device:
-            raise ValueError("expected the 9 float64 MR-STFT partial sums on this exchange's device")
-        nv.check(nv.lib().se_mrstft_exchange_value(sums.data_ptr(), self.ptrs, self.world, self.rank, global_rows, nsample,
-                                                   loss.data_ptr() if loss is not None else None, stream))
+        if sums.dtype != torch.float64 or sums.numel() not in (9, 10) or sums.device != self.device:
+            raise ValueError("expected the 9 (or 9 + row count) float64 MR-STFT partial sums on this exchange's device")
+        lp = loss.data_ptr() if loss is not None else None
+        if sums.numel() == 10:
+            nv.check(nv.lib().se_mrstft_exchange_rows_value(sums.data_ptr(), self.ptrs, self.world, self.rank, nsample, lp, stream))
+        else:
+            nv.check(nv.lib().se_mrstft_exchange_value(sums.data_ptr(), self.ptrs, self.world, self.rank, global_rows, nsample, lp, stream))
 
     def close(self):
         from . import _native as nv
@@ -103,7 +109,21 @@ class PeerExchange:
                 self.local = None
 
 
-_exchanges = {}
+# One PeerExchange per (process group, device).  Keyed on the group OBJECT through a WeakKeyDictionary: destroying a
+# group drops its entry (and closes the IPC mappings) instead of leaving a stale one behind an id() that a later group
+# may reuse.
+import weakref
+
+_exchanges = weakref.WeakKeyDictionary()
+
+
+def close_exchanges(group=None):
+    """Close the peer exchanges of `group` (or of every group): call before dist.destroy_process_group()."""
+    groups = [group] if group is not None else list(_exchanges.keys())
+    for g in groups:
+        for px in (_exchanges.pop(g, None) or {}).values():
+            if px is not None:
+                px.close()
 
 
 def peer_exchange(group, device):
@@ -112,9 +132,10 @@ def peer_exchange(group, device):
     node, or when any rank could not map its peers; the decision is taken jointly so that all ranks agree."""
     import os
     import torch.distributed as dist
-    key = (id(group), torch.device(device).index)
-    if key in _exchanges:
-        return _exchanges[key]
+    per_group = _exchanges.setdefault(group, {})
+    key = torch.device(device).index
+    if key in per_group:
+        return per_group[key]
     px, ok = None, os.environ.get("SE_P2P_EXCHANGE", "1") != "0"
     if ok:
         try:
@@ -131,7 +152,7 @@ def peer_exchange(group, device):
         if px is not None:
             px.close()
         px = None
-    _exchanges[key] = px
+    per_group[key] = px
     return px
 
 

@@ -13,25 +13,32 @@ import torch
 from . import ops
 
 
-def loss_mrstft(enhanced, sources, group=None, global_rows=None):
+def loss_mrstft(enhanced, sources, group=None, global_rows=None, scale_grad_by_world=False):
     """enhanced, sources: waveforms [B,(S,)C,N] (any leading dims).  Gradient flows to `enhanced`.
 
-    group: optional torch.distributed process group; when given, the 9 partial sums are
-    all-reduced (the path's only exchange step) so every rank gets the batch-global loss.
+    group: optional torch.distributed process group; when given, the partial sums AND the row counts of all ranks are
+    summed in the path's only exchange step, so every rank gets the batch-global loss with the true denominator even
+    when the ranks hold different numbers of rows (`global_rows` is accepted for compatibility and ignored).
+
+    Gradient scale under data parallelism: each rank's gradient is d(GLOBAL loss)/d(its local rows).  Summed over
+    ranks that is the single-GPU gradient.  DistributedDataParallel AVERAGES parameter gradients over ranks, so a
+    model trained with DDP sees 1/world of the single-GPU gradient; pass scale_grad_by_world=True (multiplies the
+    backward by the world size, leaves the loss value alone) to get the single-GPU gradient after DDP's averaging.
     """
     if enhanced.shape != sources.shape:
         raise ValueError(f"shape mismatch {tuple(enhanced.shape)} vs {tuple(sources.shape)}")
     n = enhanced.shape[-1]
-    return ops.mrstft_loss_rows(enhanced.reshape(-1, n), sources.reshape(-1, n), group, global_rows)
+    return ops.mrstft_loss_rows(enhanced.reshape(-1, n), sources.reshape(-1, n), group, scale_grad_by_world)
 
 
 class MRSTFTLoss(torch.nn.Module):
-    def __init__(self, group=None):
+    def __init__(self, group=None, scale_grad_by_world=False):
         super().__init__()
         self.group = group
+        self.scale_grad_by_world = scale_grad_by_world
 
     def forward(self, enhanced, sources):
-        return loss_mrstft(enhanced, sources, self.group)
+        return loss_mrstft(enhanced, sources, self.group, scale_grad_by_world=self.scale_grad_by_world)
 
 
 def loss_spectral(enhanced_spec, sources_wave, config, kind="mse", group=None):

@@ -143,34 +143,33 @@ def mask_apply(spec, mask, mode, pre_tanh=False):
 
 
 class _MRSTFT(torch.autograd.Function):
+    """Utterance-sharded MR-STFT loss (group given).  The exchange step carries 10 doubles: the 9 partial sums and this
+    rank's row count, so the mean's denominator is the TRUE global row count even when the shards are uneven
+    (n_utterances % world != 0) -- it never leaves the device (no host sync, no guess like rows * world)."""
+
     @staticmethod
-    def forward(ctx, est, ref, group, global_rows_hint):
+    def forward(ctx, est, ref, group, grad_scale):
         nv.require_cuda_f32(est, ref)
         rows, n = est.shape
         L = nv.lib()
+        import torch.distributed as dist
+        from . import distributed as sed
         ws = torch.empty(max(int(L.se_mrstft_workspace_bytes(rows, n)), 8), dtype=torch.uint8, device=est.device)
-        sums = torch.empty(9, dtype=torch.float64, device=est.device)
+        sums = torch.empty(10, dtype=torch.float64, device=est.device)
+        sums[9] = float(rows)                                   # this rank's rows; the exchange leaves the global count
         loss = torch.empty((), dtype=torch.float32, device=est.device)
-        global_rows = rows
         with nv.on_device(est.device):
             st = nv.stream_ptr(est.device)
             nv.check(L.se_mrstft_loss_fwd(est.data_ptr(), ref.data_ptr(), rows, n, sums.data_ptr(), ws.data_ptr(), st))
-            px = None
-            if group is not None:
-                import torch.distributed as dist
-                from . import distributed as sed
-                # the one exchange step of the path: 9 partial sums, no host sync.
-                # Utterance sharding gives every rank the same row count unless told otherwise.
-                global_rows = global_rows_hint or rows * dist.get_world_size(group)
-                px = sed.peer_exchange(group, est.device)
-                if px is None:
-                    dist.all_reduce(sums, group=group)      # NCCL: multi-node groups, or no peer access
+            # the one exchange step of the path (SURVEY 8e), no host sync
+            px = sed.peer_exchange(group, est.device)
             if px is not None:
-                px.exchange_value(sums, global_rows, n, loss, st)   # exchange + value in one kernel over peer memory
+                px.exchange_value(sums, None, n, loss, st)      # exchange + value in one kernel over peer memory
             else:
-                nv.check(L.se_mrstft_loss_value(sums.data_ptr(), global_rows, n, loss.data_ptr(), st))
+                dist.all_reduce(sums, group=group)              # NCCL: multi-node groups, or no peer access
+                nv.check(L.se_mrstft_loss_value_dev(sums.data_ptr(), n, loss.data_ptr(), st))
         ctx.save_for_backward(est, ws, sums)
-        ctx.global_rows = global_rows
+        ctx.grad_scale = float(grad_scale)
         return loss
 
     @staticmethod
@@ -178,19 +177,33 @@ class _MRSTFT(torch.autograd.Function):
         est, ws, sums = ctx.saved_tensors
         rows, n = est.shape
         gout = gout.contiguous().float()
+        if ctx.grad_scale != 1.0:
+            gout = gout * ctx.grad_scale
         g = torch.empty_like(est)
         with nv.on_device(est.device):
+            # global_rows = 0: the kernels read the global row count from sums[9]
             nv.check(nv.lib().se_mrstft_loss_bwd(est.data_ptr(), ws.data_ptr(), sums.data_ptr(), gout.data_ptr(),
-                                                 ctx.global_rows, rows, n, g.data_ptr(), nv.stream_ptr(est.device)))
+                                                 0, rows, n, g.data_ptr(), nv.stream_ptr(est.device)))
         return g, None, None, None
 
 
-def mrstft_loss_rows(est_rows, ref_rows, group=None, global_rows=None):
+def mrstft_loss_rows(est_rows, ref_rows, group=None, scale_grad_by_world=False):
     if ref_rows.requires_grad:
         raise NotImplementedError("loss_mrstft: gradient flows to `enhanced` only (targets must not require grad)")
     if group is None:
         return nv.torch_ops().mrstft_loss(est_rows, ref_rows)
-    return _MRSTFT.apply(_as_f32(est_rows).contiguous(), _as_f32(ref_rows).contiguous(), group, global_rows)
+    import torch.distributed as dist
+    scale = float(dist.get_world_size(group)) if scale_grad_by_world else 1.0
+    return _MRSTFT.apply(_as_f32(est_rows).contiguous(), _as_f32(ref_rows).contiguous(), group, scale)
+
+
+def _global_count(local_count, total, group):
+    """Sum (total, local element count) over the group in one all-reduce; returns (total, count) as device doubles --
+    uneven shards get the true denominator without a host sync."""
+    import torch.distributed as dist
+    both = torch.stack([total.reshape(()), torch.tensor(float(local_count), dtype=torch.float64, device=total.device)])
+    dist.all_reduce(both, group=group)
+    return both[0], both[1]
 
 
 class _SpectralLoss(torch.autograd.Function):
@@ -205,25 +218,30 @@ class _SpectralLoss(torch.autograd.Function):
             nv.check(L.se_spectral_loss_fwd(enh.data_ptr(), target.data_ptr(), rows, n, n_fft, hop, win_length,
                                             1.0 / win_length, kind, total.data_ptr(), ws.data_ptr(),
                                             nv.stream_ptr(enh.device)))
-        global_rows = rows
+        count = rows * (n_fft // 2 + 1) * (1 + n // hop) * 2
+        ratio = None
         if group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(total, group=group)
-            global_rows = rows * dist.get_world_size(group)
-        ctx.save_for_backward(enh, target)
-        ctx.cfg = (n_fft, hop, win_length, kind, global_rows)
-        count = global_rows * (n_fft // 2 + 1) * (1 + n // hop) * 2
-        return (total / count).float()
+            # mean over the GLOBAL element count, summed on the device together with the partial sums (uneven shards)
+            total, gcount = _global_count(count, total, group)
+            ratio = (count / gcount).float()                    # local / global: folded into the upstream gradient
+            loss = (total / gcount).float()
+        else:
+            loss = (total / count).float()
+        ctx.save_for_backward(enh, target, ratio)
+        ctx.cfg = (n_fft, hop, win_length, kind)
+        return loss
 
     @staticmethod
     def backward(ctx, gout):
-        enh, target = ctx.saved_tensors
-        n_fft, hop, win_length, kind, global_rows = ctx.cfg
+        enh, target, ratio = ctx.saved_tensors
+        n_fft, hop, win_length, kind = ctx.cfg
         rows, n = target.shape
         gout = gout.contiguous().float()
+        if ratio is not None:
+            gout = gout * ratio                                 # d mean / d enh = (1 / global count) d sum / d enh
         g = torch.empty_like(enh)
         with nv.on_device(enh.device):
-            nv.check(nv.lib().se_spectral_loss_bwd(enh.data_ptr(), target.data_ptr(), gout.data_ptr(), global_rows, rows, n,
+            nv.check(nv.lib().se_spectral_loss_bwd(enh.data_ptr(), target.data_ptr(), gout.data_ptr(), rows, rows, n,
                                                    n_fft, hop, win_length, 1.0 / win_length, kind, g.data_ptr(),
                                                    nv.stream_ptr(enh.device)))
         return g, None, None, None, None, None, None
@@ -280,22 +298,25 @@ class _PSA(torch.autograd.Function):
         with nv.on_device(enh.device):
             nv.check(L.se_psa_loss_fwd(enh.data_ptr(), tgt.data_ptr(), mix.data_ptr(), count, total.data_ptr(), ws.data_ptr(),
                                        nv.stream_ptr(enh.device)))
-        global_count = count
+        ratio = None
         if group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(total, group=group)
-            global_count = count * dist.get_world_size(group)
-        ctx.save_for_backward(enh, tgt, mix)
-        ctx.global_count = global_count
-        return (total / global_count).float()
+            total, gcount = _global_count(count, total, group)
+            ratio = (count / gcount).float()
+            loss = (total / gcount).float()
+        else:
+            loss = (total / count).float()
+        ctx.save_for_backward(enh, tgt, mix, ratio)
+        return loss
 
     @staticmethod
     def backward(ctx, gout):
-        enh, tgt, mix = ctx.saved_tensors
+        enh, tgt, mix, ratio = ctx.saved_tensors
         g = torch.empty_like(enh)
         gout = gout.contiguous().float()
+        if ratio is not None:
+            gout = gout * ratio
         with nv.on_device(enh.device):
-            nv.check(nv.lib().se_psa_loss_bwd(enh.data_ptr(), tgt.data_ptr(), mix.data_ptr(), gout.data_ptr(), ctx.global_count,
+            nv.check(nv.lib().se_psa_loss_bwd(enh.data_ptr(), tgt.data_ptr(), mix.data_ptr(), gout.data_ptr(), enh.numel() // 2,
                                               enh.numel() // 2, g.data_ptr(), nv.stream_ptr(enh.device)))
         return g, None, None, None
 

@@ -30,13 +30,15 @@ def _worker(rank, world, port, nsample, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import spectral_oracle as oref
     g = torch.Generator().manual_seed(4)
-    ref = torch.randn(6, 1, nsample, generator=g)
-    est = ref + 0.2 * torch.randn(6, 1, nsample, generator=g)
-    sl = sed.shard_rows(6, world, rank)
+    ref = torch.randn(7, 1, nsample, generator=g)
+    est = ref + 0.2 * torch.randn(7, 1, nsample, generator=g)
+    sl = sed.shard_rows(7, world, rank)                  # UNEVEN shards: 4 + 3 rows
     parts = oref.mrstft_partials_ref(est[sl], ref[sl])
-    sums = torch.tensor([v for p in parts for v in p[:3]], dtype=torch.float64)
+    # the exchange carries the 9 sums AND this rank's row count: no rank guesses the global count as rows * world
+    sums = torch.tensor([v for p in parts for v in p[:3]] + [float(sl.stop - sl.start)], dtype=torch.float64)
     sed.all_reduce_sums(sums)
-    out[rank] = sed.loss_from_sums(sums, 6, nsample)
+    assert int(sums[9]) == 7
+    out[rank] = sed.loss_from_sums(sums[:9], int(sums[9]), nsample)
     dist.destroy_process_group()
 
 
@@ -50,8 +52,8 @@ def test_two_rank_loss_equals_global_loss():
     mp.spawn(_worker, args=(2, port, nsample, out), nprocs=2, join=True)
     from oracle import spectral_oracle as oref
     g = torch.Generator().manual_seed(4)
-    ref = torch.randn(6, 1, nsample, generator=g)
-    est = ref + 0.2 * torch.randn(6, 1, nsample, generator=g)
+    ref = torch.randn(7, 1, nsample, generator=g)
+    est = ref + 0.2 * torch.randn(7, 1, nsample, generator=g)
     want = float(oref.mrstft_loss_ref(est, ref))
     assert abs(out[0] - out[1]) < 1e-12
     assert abs(out[0] - want) / want < 1e-5
