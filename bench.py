@@ -742,6 +742,20 @@ def run_ours(args):
             consumed[j].record(main)
             return raw.grad
 
+        # the host's own ceiling: the same three pinned uploads back to back with no compute (all ranks at once) -- what
+        # the PCIe / host-memory path of this box can deliver per GPU at this N
+        sync_all()
+        ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(copy_stream):
+            ca.record(copy_stream)
+            for i in range(10):
+                for d, h in zip(dbuf[i & 1], (hx[i & 1], hc[i & 1], hm[i & 1])):
+                    d.copy_(h, non_blocking=True)
+            cb.record(copy_stream)
+        sync_all()
+        copy_only = torch.tensor([(hx[0].numel() + hc[0].numel() + hm[0].numel()) * 4 * 10 / (ca.elapsed_time(cb) * 1e-3) * 1e-9], device=dev)
+        if group is not None:
+            dist.all_reduce(copy_only, op=dist.ReduceOp.MIN)
         for j in range(2):
             consumed[j].record(main)
         e2e_steps = max(5, min(args.steps, 30))
@@ -776,8 +790,11 @@ def run_ours(args):
                "h2d_gbs": round(h2d / (e2e_ms * 1e-3) * 1e-9, 1),
                "h2d_gbs_per_rank": [round(float(v[0]), 1) for v in gathered],
                "numa_node_per_rank": [int(v[1]) for v in gathered], "placement_rank0": placement,
-               "note": "copy-bound: the 98.7 MB/step of pinned-host inputs (mixture, clean, raw mask) saturate PCIe; "
-                       "kernels overlap underneath on the compute stream",
+               "h2d_copy_only_gbs_min_rank": round(float(copy_only), 1),
+               "note": "copy-bound: the 98.7 MB/step of pinned-host inputs (mixture, clean, raw mask) saturate the host-to-device path; "
+                       "kernels overlap underneath on the compute stream.  h2d_copy_only_gbs_min_rank is the same uploads with no "
+                       "compute at this N: the pool's 8-GPU boxes are VMs with ONE NUMA node (nvidia-smi topo: all GPUs NUMA 0, "
+                       "cpus 0-31), so per-rank placement cannot help and the aggregate host ceiling (~185 GB/s) bounds e2e scaling",
                "api": {"tail": "stft_custom/apply_mask_istft", "dropin": "stft_custom/apply_mask/istft_custom",
                        "fused": "enhance"}[comp] + "/loss_mrstft + autograd; pinned host inputs, copy stream double-buffered",
                "loss": float(hloss)}

@@ -239,6 +239,29 @@ int se_overlap_add_bwd(const float* gout, float* gsignal, int64_t rows, int64_t 
  * x [rows,N] -> spec [rows, 2F, T], T = (N + 2(win_len-win_inc) - win_len)/win_inc + 1, Hann
  * window, zero padding, frame zero-extended at the END to fft_len.  Supported: fft_len 512,
  * win_len <= fft_len, even win_inc. */
+/* Any window instead of Hann (the reference takes a scipy.signal.get_window type, dccrn.py:651-655): the host computes
+ * the window values once, se_register_window returns an id > 0 for them (identical values share an id), and the *_w
+ * variants of the transforms take it (0 = the built-in periodic Hann). */
+int se_register_window(const double* values, int win_len);
+int se_conv_stft_fwd_w(const float* x, float* spec, int64_t rows, int64_t nsample, int win_len, int win_inc, int fft_len,
+                       int window_id, void* stream);
+int se_conv_istft_fwd_w(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t out_len, int win_len, int win_inc,
+                        int fft_len, int window_id, void* stream);
+int se_conv_istft_bwd_w(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t out_len, int win_len, int win_inc,
+                        int fft_len, int window_id, void* stream);
+int se_conv_mask_istft_fwd_w(const float* spec, const float* mask_re, const float* mask_im, float* y, int64_t rows,
+                             int64_t nframe, int64_t out_len, int win_len, int win_inc, int fft_len, int mode, int window_id,
+                             void* stream);
+int se_conv_mask_istft_bwd_w(const float* gy, const float* spec, const float* mask_re, const float* mask_im, float* gmask_re,
+                             float* gmask_im, int64_t rows, int64_t nframe, int64_t out_len, int win_len, int win_inc,
+                             int fft_len, int mode, int window_id, void* stream);
+/* ConvSTFT(feature_type='real') epilogue (mags, phase = sqrt(re^2+im^2), atan2(im, re), dccrn.py:696-701) and
+ * ConviSTFT(inputs, phase) prologue (cat([mags cos, mags sin], 1), :729-732) on the planar [rows, 2*nbin, nframe] layout,
+ * one launch each; the last is the gradient of the prologue wrt (mags, phase). */
+int se_polar_from_planar(const float* spec, float* mags, float* phase, int64_t rows, int64_t nbin, int64_t nframe, void* stream);
+int se_planar_from_polar(const float* mags, const float* phase, float* spec, int64_t rows, int64_t nbin, int64_t nframe, void* stream);
+int se_planar_from_polar_bwd(const float* mags, const float* phase, const float* gspec, float* gmags, float* gphase, int64_t rows,
+                             int64_t nbin, int64_t nframe, void* stream);
 int se_conv_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int win_len, int win_inc,
                      int fft_len, void* stream);
 /* spec [rows,2F,T] -> y [rows,out_len]; out_len = length if length > 0 else natural

@@ -31,6 +31,8 @@ EXPORTS = (
     "se_mask_planar_fwd", "se_mask_planar_bwd", "se_conv_mask_istft_fwd", "se_conv_mask_istft_bwd",
     "se_p2p_create", "se_p2p_open", "se_p2p_close", "se_p2p_destroy", "se_mrstft_exchange_value",
     "se_mrstft_exchange_rows_value", "se_mrstft_loss_value_dev",
+    "se_register_window", "se_conv_stft_fwd_w", "se_conv_istft_fwd_w", "se_conv_istft_bwd_w", "se_conv_mask_istft_fwd_w",
+    "se_conv_mask_istft_bwd_w", "se_polar_from_planar", "se_planar_from_polar", "se_planar_from_polar_bwd",
 )
 
 MASK_MODES = {"real": 0, "E": 1, "C": 2, "R": 3}
@@ -175,6 +177,15 @@ def lib():
             L.se_conv_stft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _PTR]
             L.se_conv_istft_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]
             L.se_conv_istft_bwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _PTR]
+            L.se_register_window.argtypes = [_PTR, _INT]
+            L.se_conv_stft_fwd_w.argtypes = [_PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _INT, _PTR]
+            L.se_conv_istft_fwd_w.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _PTR]
+            L.se_conv_istft_bwd_w.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _PTR]
+            L.se_conv_mask_istft_fwd_w.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
+            L.se_conv_mask_istft_bwd_w.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _INT, _PTR]
+            L.se_polar_from_planar.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _PTR]
+            L.se_planar_from_polar.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _PTR]
+            L.se_planar_from_polar_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _PTR]
             L.se_mask_planar_fwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _PTR]
             L.se_mask_planar_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _PTR]
             L.se_conv_mask_istft_fwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _INT, _INT, _INT, _INT, _PTR]

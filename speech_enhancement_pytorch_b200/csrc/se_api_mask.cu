@@ -3,7 +3,80 @@
 
 using namespace se;
 
+// ---- DCCRN's polar feature (ConvSTFT feature_type='real', src/model/dccrn.py:696-701) and its inverse
+// (ConviSTFT(inputs, phase), :729-732) as single launches on the planar [rows, 2F, T] layout, full-precision
+// sqrt / atan2 / sincos (no stack / cat / cos / sin / mul passes).  plane = F*T elements per row.
+static __global__ void __launch_bounds__(256) k_polar_from_planar(const float* __restrict__ spec, float* __restrict__ mags,
+                                                                  float* __restrict__ phase, int64_t plane, int bpr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t row = blockIdx.x / bpr;
+    const int chunk = blockIdx.x - (int)row * bpr;
+    for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < plane; i += (int64_t)bpr * blockDim.x) {
+        const float re = __ldg(spec + row * 2 * plane + i), im = __ldg(spec + row * 2 * plane + plane + i);
+        mags[row * plane + i] = sqrtf(re * re + im * im);
+        phase[row * plane + i] = atan2f(im, re);
+    }
+}
+static __global__ void __launch_bounds__(256) k_planar_from_polar(const float* __restrict__ mags, const float* __restrict__ phase,
+                                                                  float* __restrict__ spec, int64_t plane, int bpr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t row = blockIdx.x / bpr;
+    const int chunk = blockIdx.x - (int)row * bpr;
+    for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < plane; i += (int64_t)bpr * blockDim.x) {
+        float sn, cs;
+        sincosf(__ldg(phase + row * plane + i), &sn, &cs);
+        const float m = __ldg(mags + row * plane + i);
+        spec[row * 2 * plane + i] = m * cs;
+        spec[row * 2 * plane + plane + i] = m * sn;
+    }
+}
+// gspec [rows, 2F, T] -> gmags = gre cos + gim sin, gphase = mags (gim cos - gre sin)
+static __global__ void __launch_bounds__(256) k_planar_from_polar_bwd(const float* __restrict__ mags, const float* __restrict__ phase,
+                                                                      const float* __restrict__ gspec, float* __restrict__ gmags,
+                                                                      float* __restrict__ gphase, int64_t plane, int bpr) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int64_t row = blockIdx.x / bpr;
+    const int chunk = blockIdx.x - (int)row * bpr;
+    for (int64_t i = (int64_t)chunk * blockDim.x + threadIdx.x; i < plane; i += (int64_t)bpr * blockDim.x) {
+        float sn, cs;
+        sincosf(__ldg(phase + row * plane + i), &sn, &cs);
+        const float gre = __ldg(gspec + row * 2 * plane + i), gim = __ldg(gspec + row * 2 * plane + plane + i);
+        gmags[row * plane + i] = gre * cs + gim * sn;
+        gphase[row * plane + i] = __ldg(mags + row * plane + i) * (gim * cs - gre * sn);
+    }
+}
+
+static int planar_blocks_per_row(int64_t rows, int64_t plane);
+
 extern "C" {
+
+int se_polar_from_planar(const float* spec, float* mags, float* phase, int64_t rows, int64_t nbin, int64_t nframe, void* stream) {
+    if (!spec || !mags || !phase || rows <= 0 || nbin <= 0 || nframe <= 0) return fail(SE_ERR_BAD_ARG, "null pointer or empty tensor");
+    const int64_t plane = nbin * nframe;
+    const int bpr = planar_blocks_per_row(rows, plane);
+    cudaError_t e = launch(k_polar_from_planar, (unsigned)(rows * bpr), 256u, 0, (cudaStream_t)stream, spec, mags, phase, plane, bpr);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_polar_from_planar launch");
+}
+int se_planar_from_polar(const float* mags, const float* phase, float* spec, int64_t rows, int64_t nbin, int64_t nframe, void* stream) {
+    if (!spec || !mags || !phase || rows <= 0 || nbin <= 0 || nframe <= 0) return fail(SE_ERR_BAD_ARG, "null pointer or empty tensor");
+    const int64_t plane = nbin * nframe;
+    const int bpr = planar_blocks_per_row(rows, plane);
+    cudaError_t e = launch(k_planar_from_polar, (unsigned)(rows * bpr), 256u, 0, (cudaStream_t)stream, mags, phase, spec, plane, bpr);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_planar_from_polar launch");
+}
+int se_planar_from_polar_bwd(const float* mags, const float* phase, const float* gspec, float* gmags, float* gphase, int64_t rows,
+                             int64_t nbin, int64_t nframe, void* stream) {
+    if (!mags || !phase || !gspec || !gmags || !gphase || rows <= 0 || nbin <= 0 || nframe <= 0)
+        return fail(SE_ERR_BAD_ARG, "null pointer or empty tensor");
+    const int64_t plane = nbin * nframe;
+    const int bpr = planar_blocks_per_row(rows, plane);
+    cudaError_t e = launch(k_planar_from_polar_bwd, (unsigned)(rows * bpr), 256u, 0, (cudaStream_t)stream, mags, phase, gspec, gmags,
+                           gphase, plane, bpr);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_planar_from_polar_bwd launch");
+}
 
 int se_mask_fwd(const float* spec, const float* mask, float* out, int64_t count, int mode, int pre_tanh, void* stream) {
     if (!spec || !mask || !out || count <= 0) return fail(SE_ERR_BAD_ARG, "null pointer or empty tensor");
@@ -30,6 +103,7 @@ int se_mask_bwd(const float* spec, const float* mask, const float* gout, float* 
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mask_bwd launch");
 }
 
+}  // extern "C"
 // blocks per row: enough to fill the GPU a few times over, at least one, never more than the row has 256-element tiles
 static int planar_blocks_per_row(int64_t rows, int64_t plane) {
     const int64_t tiles = (plane + 255) / 256;
@@ -37,6 +111,7 @@ static int planar_blocks_per_row(int64_t rows, int64_t plane) {
     want = want < 1 ? 1 : (want > tiles ? tiles : want);
     return (int)want;
 }
+extern "C" {
 
 #define SE_DISPATCH_PLANAR(mode, CALL)                                                   \
     do {                                                                                 \

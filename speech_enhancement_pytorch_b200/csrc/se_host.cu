@@ -21,28 +21,51 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 // ------------------------------------------------------------------ constant tables
 struct TableKey {
-    int dev, n, hop, win_len, front;
+    int dev, n, hop, win_len, front, window_id;
     uint32_t scale_bits;
     bool operator<(const TableKey& o) const {
-        return std::tie(dev, n, hop, win_len, front, scale_bits) <
-               std::tie(o.dev, o.n, o.hop, o.win_len, o.front, o.scale_bits);
+        return std::tie(dev, n, hop, win_len, front, window_id, scale_bits) <
+               std::tie(o.dev, o.n, o.hop, o.win_len, o.front, o.window_id, o.scale_bits);
     }
 };
 static std::mutex g_mu;
 static std::map<TableKey, Tables> g_tables;
 
-static void host_window(int n, int win_len, bool front, std::vector<double>& w) {
+// Caller-supplied windows (DCCRN's ConvSTFT takes any scipy.signal.get_window type, src/model/dccrn.py:651-655): the
+// host side computes the window once and registers its values; id 0 is the built-in periodic Hann.
+static std::mutex g_win_mu;
+static std::vector<std::vector<double>> g_windows;
+
+int register_window(const double* values, int win_len) {
+    if (!values || win_len < 2 || win_len > 2048) return fail(SE_ERR_BAD_ARG, "window: need 2 <= win_len <= 2048 values");
+    std::lock_guard<std::mutex> lock(g_win_mu);
+    for (size_t i = 0; i < g_windows.size(); ++i)
+        if ((int)g_windows[i].size() == win_len && std::memcmp(g_windows[i].data(), values, sizeof(double) * win_len) == 0)
+            return (int)i + 1;
+    if (g_windows.size() >= 4096) return fail(SE_ERR_BAD_ARG, "too many distinct windows registered");
+    g_windows.emplace_back(values, values + win_len);
+    return (int)g_windows.size();
+}
+
+static bool host_window(int n, int win_len, bool front, std::vector<double>& w, int window_id = 0) {
     w.assign(n, 0.0);
     const int left = front ? 0 : (n - win_len) / 2;
+    if (window_id > 0) {
+        std::lock_guard<std::mutex> lock(g_win_mu);
+        if (window_id > (int)g_windows.size() || (int)g_windows[window_id - 1].size() != win_len) return false;
+        for (int j = 0; j < win_len; ++j) w[left + j] = g_windows[window_id - 1][j];
+        return true;
+    }
     const double two_pi = 6.283185307179586476925286766559;
     for (int j = 0; j < win_len; ++j) w[left + j] = 0.5 - 0.5 * std::cos(two_pi * j / win_len);
+    return true;
 }
 
 // `scale` multiplies the window; front=true puts a short window at the start of the frame (DCCRN)
-int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out) {
+int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out, int window_id) {
     int dev = 0;
     cudaGetDevice(&dev);
-    TableKey key{dev, n, hop, win_len, front ? 1 : 0, 0};
+    TableKey key{dev, n, hop, win_len, front ? 1 : 0, window_id, 0};
     std::memcpy(&key.scale_bits, &scale, 4);
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_tables.find(key);
@@ -50,7 +73,7 @@ int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out
     const int M = n / 2;
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<double> w;
-    host_window(n, win_len, front, w);
+    if (!host_window(n, win_len, front, w, window_id)) return fail(SE_ERR_BAD_ARG, "unknown window id (or its length differs from win_length)");
     std::vector<float> win(n), w2(n), inv_env(hop);
     std::vector<float2> tw(M), twn(M);
     for (int j = 0; j < n; ++j) {

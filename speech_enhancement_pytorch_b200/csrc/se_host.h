@@ -12,7 +12,9 @@ int cuda_fail(cudaError_t e, const char* what);
 const char* last_error();
 // constant tables per (device, n, hop, win_len, placement, scale); `scale` multiplies the window,
 // front=true puts a short window at the start of the frame (DCCRN)
-int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out);
+int get_tables(int n, int hop, int win_len, bool front, float scale, Tables& out, int window_id = 0);
+// window_id > 0: values registered with se_register_window (any window type); 0: periodic Hann
+int register_window(const double* values, int win_len);
 // torch.istft's "window overlap add min" check on the host (no device sync)
 bool envelope_ok(int n, int hop, int win_len, bool front, int64_t T, int64_t lo, int64_t hi, double floor_);
 void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_per_group);

@@ -27,12 +27,15 @@ void check(int rc) {
     TORCH_CHECK(false, "se_b200[", rc, "]: ", msg);
 }
 
-// CUDA-only, fp32 at the C-ABI: half / bf16 inputs are up-cast ("bf16 model, fp32 spectra", BASELINE cfg 4)
+// CUDA-only, fp32 at the C-ABI: half / bf16 inputs are up-cast ("bf16 model, fp32 spectra", BASELINE cfg 4); float64
+// inputs (the reference passes dtype=tensor.dtype to its window and works in double, src/evaluate.py:113,147) are
+// computed in fp32 and the result is returned as float64 -- the casts are ordinary differentiable ops, so gradients
+// come back in the input's dtype.
 Tensor prep(const Tensor& t, const char* what) {
     TORCH_CHECK(t.is_cuda(), "speech_enhancement_pytorch_b200 runs on CUDA tensors only (hand-written sm_100a kernels; "
                              "there is no CPU fallback): ", what, " is on ", t.device());
     Tensor r = t;
-    if (r.scalar_type() == at::kHalf || r.scalar_type() == at::kBFloat16) r = r.to(at::kFloat);
+    if (r.scalar_type() == at::kHalf || r.scalar_type() == at::kBFloat16 || r.scalar_type() == at::kDouble) r = r.to(at::kFloat);
     TORCH_CHECK_TYPE(r.scalar_type() == at::kFloat, "expected float32 tensors, got ", r.scalar_type(), " for ", what);
     return r.contiguous();
 }
@@ -225,15 +228,17 @@ Tensor op_stft(const Tensor& x_in, int64_t n_fft, int64_t hop, int64_t win, doub
     check_cfg(n_fft, hop, win);
     TORCH_CHECK_VALUE(x_in.dim() == 2, "se_b200::stft expects [rows, N]");
     const Tensor x = prep(x_in, "input");
-    if (!needs_grad({&x})) return stft_raw(x, n_fft, hop, win, scale);        // inference: no autograd node
-    return StftFn::apply(x, n_fft, hop, win, scale);
+    const Tensor out = needs_grad({&x}) ? StftFn::apply(x, n_fft, hop, win, scale)
+                                        : stft_raw(x, n_fft, hop, win, scale);        // inference: no autograd node
+    return x_in.scalar_type() == at::kDouble ? out.to(at::kDouble) : out;
 }
 Tensor op_istft(const Tensor& spec_in, int64_t length, int64_t n_fft, int64_t hop, int64_t win, double scale) {
     check_cfg(n_fft, hop, win);
     TORCH_CHECK_VALUE(spec_in.dim() == 4 && spec_in.size(3) == 2, "se_b200::istft expects [rows, F, T, 2]");
     const Tensor spec = prep(spec_in, "spectrum");
-    if (!needs_grad({&spec})) return istft_raw(spec, length, n_fft, hop, win, scale);
-    return IstftFn::apply(spec, length, n_fft, hop, win, scale);
+    const Tensor out = needs_grad({&spec}) ? IstftFn::apply(spec, length, n_fft, hop, win, scale)
+                                           : istft_raw(spec, length, n_fft, hop, win, scale);
+    return spec_in.scalar_type() == at::kDouble ? out.to(at::kDouble) : out;
 }
 Tensor op_mask(const Tensor& spec, const Tensor& mask, int64_t mode, bool pre_tanh) {
     return MaskFn::apply(prep(spec, "spectrum"), prep(mask, "mask"), mode, pre_tanh);

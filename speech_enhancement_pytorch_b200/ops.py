@@ -393,74 +393,131 @@ def row_dots(s1_rows, s2_rows):
 
 
 # ------------------------------------------------------------------ DCCRN conv transforms
-def conv_stft_rows(x, win_len, win_inc, fft_len):
+def register_window(values):
+    """Register window values (any scipy.signal.get_window type, computed on the host) with the library and return
+    their id (> 0; identical values share one) for the DCCRN transforms' `window_id` argument."""
+    import ctypes
+    import numpy as np
+    w = np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+    wid = nv.lib().se_register_window(w.ctypes.data_as(ctypes.c_void_p), int(w.shape[0]))
+    if wid <= 0:
+        nv.check(wid)
+    return int(wid)
+
+
+def conv_stft_rows(x, win_len, win_inc, fft_len, window_id=0):
     nv.require_cuda_f32(x)
     rows, n = x.shape
     nt = (n + 2 * (win_len - win_inc) - win_len) // win_inc + 1
     out = torch.empty((rows, 2 * (fft_len // 2 + 1), nt), dtype=torch.float32, device=x.device)
     with nv.on_device(x.device):
-        nv.check(nv.lib().se_conv_stft_fwd(x.data_ptr(), out.data_ptr(), rows, n, win_len, win_inc, fft_len,
-                                           nv.stream_ptr(x.device)))
+        nv.check(nv.lib().se_conv_stft_fwd_w(x.data_ptr(), out.data_ptr(), rows, n, win_len, win_inc, fft_len, window_id,
+                                             nv.stream_ptr(x.device)))
     return out
+
+
+def polar_from_planar(spec):
+    """[rows, 2F, T] planar spectrum -> (mags, phase) [rows, F, T] in one launch (ConvSTFT feature_type='real')."""
+    nv.require_cuda_f32(spec)
+    rows, nf2, nt = spec.shape
+    mags = torch.empty((rows, nf2 // 2, nt), dtype=torch.float32, device=spec.device)
+    phase = torch.empty_like(mags)
+    with nv.on_device(spec.device):
+        nv.check(nv.lib().se_polar_from_planar(spec.data_ptr(), mags.data_ptr(), phase.data_ptr(), rows, nf2 // 2, nt,
+                                               nv.stream_ptr(spec.device)))
+    return mags, phase
+
+
+class _PlanarFromPolar(torch.autograd.Function):
+    """cat([mags cos(phase), mags sin(phase)], 1) (ConviSTFT(inputs, phase), dccrn.py:729-732) in one launch each way."""
+
+    @staticmethod
+    def forward(ctx, mags, phase):
+        nv.require_cuda_f32(mags, phase)
+        rows, nf, nt = mags.shape
+        spec = torch.empty((rows, 2 * nf, nt), dtype=torch.float32, device=mags.device)
+        with nv.on_device(mags.device):
+            nv.check(nv.lib().se_planar_from_polar(mags.data_ptr(), phase.data_ptr(), spec.data_ptr(), rows, nf, nt,
+                                                   nv.stream_ptr(mags.device)))
+        ctx.save_for_backward(mags, phase)
+        return spec
+
+    @staticmethod
+    def backward(ctx, g):
+        mags, phase = ctx.saved_tensors
+        rows, nf, nt = mags.shape
+        g = g.contiguous()
+        gm, gp = torch.empty_like(mags), torch.empty_like(phase)
+        with nv.on_device(mags.device):
+            nv.check(nv.lib().se_planar_from_polar_bwd(mags.data_ptr(), phase.data_ptr(), g.data_ptr(), gm.data_ptr(), gp.data_ptr(),
+                                                       rows, nf, nt, nv.stream_ptr(mags.device)))
+        return gm, gp
+
+
+def planar_from_polar(mags, phase):
+    if mags.shape != phase.shape or mags.dim() != 3:
+        raise ValueError(f"expected mags and phase [B,F,T], got {tuple(mags.shape)} and {tuple(phase.shape)}")
+    return _PlanarFromPolar.apply(_as_f32(mags).contiguous(), _as_f32(phase).contiguous())
 
 
 class _ConvISTFT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec, out_len, win_len, win_inc, fft_len):
+    def forward(ctx, spec, out_len, win_len, win_inc, fft_len, window_id):
         nv.require_cuda_f32(spec)
         rows, _, nt = spec.shape
         y = torch.empty((rows, out_len), dtype=torch.float32, device=spec.device)
         with nv.on_device(spec.device):
-            nv.check(nv.lib().se_conv_istft_fwd(spec.data_ptr(), y.data_ptr(), rows, nt, out_len, win_len, win_inc,
-                                                fft_len, nv.stream_ptr(spec.device)))
-        ctx.cfg = (nt, win_len, win_inc, fft_len)
+            nv.check(nv.lib().se_conv_istft_fwd_w(spec.data_ptr(), y.data_ptr(), rows, nt, out_len, win_len, win_inc,
+                                                  fft_len, window_id, nv.stream_ptr(spec.device)))
+        ctx.cfg = (nt, win_len, win_inc, fft_len, window_id)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        nt, win_len, win_inc, fft_len = ctx.cfg
+        nt, win_len, win_inc, fft_len, window_id = ctx.cfg
         gy = gy.contiguous()
         rows, out_len = gy.shape
         g = torch.empty((rows, 2 * (fft_len // 2 + 1), nt), dtype=torch.float32, device=gy.device)
         with nv.on_device(gy.device):
-            nv.check(nv.lib().se_conv_istft_bwd(gy.data_ptr(), g.data_ptr(), rows, nt, out_len, win_len, win_inc,
-                                                fft_len, nv.stream_ptr(gy.device)))
-        return g, None, None, None, None
+            nv.check(nv.lib().se_conv_istft_bwd_w(gy.data_ptr(), g.data_ptr(), rows, nt, out_len, win_len, win_inc,
+                                                  fft_len, window_id, nv.stream_ptr(gy.device)))
+        return g, None, None, None, None, None
 
 
 class _ConvMaskISTFT(torch.autograd.Function):
     """ConviSTFT(apply_mask_dccrn(specs, mask_re, mask_im)) in one launch each way; gradient to the two mask planes."""
 
     @staticmethod
-    def forward(ctx, spec, mre, mim, out_len, win_len, win_inc, fft_len, mode):
+    def forward(ctx, spec, mre, mim, out_len, win_len, win_inc, fft_len, mode, window_id):
         nv.require_cuda_f32(spec, mre, mim)
         rows, _, nt = spec.shape
         y = torch.empty((rows, out_len), dtype=torch.float32, device=spec.device)
         with nv.on_device(spec.device):
-            nv.check(nv.lib().se_conv_mask_istft_fwd(spec.data_ptr(), mre.data_ptr(), mim.data_ptr(), y.data_ptr(), rows, nt,
-                                                     out_len, win_len, win_inc, fft_len, mode, nv.stream_ptr(spec.device)))
+            nv.check(nv.lib().se_conv_mask_istft_fwd_w(spec.data_ptr(), mre.data_ptr(), mim.data_ptr(), y.data_ptr(), rows, nt,
+                                                       out_len, win_len, win_inc, fft_len, mode, window_id,
+                                                       nv.stream_ptr(spec.device)))
         ctx.save_for_backward(spec, mre, mim)
-        ctx.cfg = (out_len, win_len, win_inc, fft_len, mode)
+        ctx.cfg = (out_len, win_len, win_inc, fft_len, mode, window_id)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         spec, mre, mim = ctx.saved_tensors
-        out_len, win_len, win_inc, fft_len, mode = ctx.cfg
+        out_len, win_len, win_inc, fft_len, mode, window_id = ctx.cfg
         rows, _, nt = spec.shape
         gy = gy.contiguous()
         gre, gim = torch.empty_like(mre), torch.empty_like(mim)
         with nv.on_device(spec.device):
-            nv.check(nv.lib().se_conv_mask_istft_bwd(gy.data_ptr(), spec.data_ptr(), mre.data_ptr(), mim.data_ptr(),
-                                                     gre.data_ptr(), gim.data_ptr(), rows, nt, out_len, win_len, win_inc,
-                                                     fft_len, mode, nv.stream_ptr(spec.device)))
-        return None, gre, gim, None, None, None, None, None
+            nv.check(nv.lib().se_conv_mask_istft_bwd_w(gy.data_ptr(), spec.data_ptr(), mre.data_ptr(), mim.data_ptr(),
+                                                       gre.data_ptr(), gim.data_ptr(), rows, nt, out_len, win_len, win_inc,
+                                                       fft_len, mode, window_id, nv.stream_ptr(spec.device)))
+        return None, gre, gim, None, None, None, None, None, None
 
 
-def conv_mask_istft_rows(spec, mask_real, mask_imag, out_len, win_len, win_inc, fft_len, mode):
+def conv_mask_istft_rows(spec, mask_real, mask_imag, out_len, win_len, win_inc, fft_len, mode, window_id=0):
     return _ConvMaskISTFT.apply(_as_f32(spec).contiguous(), _as_f32(mask_real).contiguous(), _as_f32(mask_imag).contiguous(),
-                                int(out_len), win_len, win_inc, fft_len, nv.MASK_MODES[mode])
+                                int(out_len), win_len, win_inc, fft_len, nv.MASK_MODES[mode], window_id)
 
 
-def conv_istft_rows(spec, out_len, win_len, win_inc, fft_len):
-    return _ConvISTFT.apply(_as_f32(spec).contiguous(), int(out_len), win_len, win_inc, fft_len)
+def conv_istft_rows(spec, out_len, win_len, win_inc, fft_len, window_id=0):
+    return _ConvISTFT.apply(_as_f32(spec).contiguous(), int(out_len), win_len, win_inc, fft_len, window_id)

@@ -181,6 +181,54 @@ def conv_istft_bwd(gy, T, win_len, win_inc, fft_len):
     return out
 
 
+def register_window(values):
+    w = np.ascontiguousarray(np.asarray(values, np.float64))
+    wid = lib().se_register_window(ptr(w), ci(w.shape[0]))
+    assert wid > 0
+    return wid
+
+
+def conv_stft_fwd_w(x, win_len, win_inc, fft_len, wid):
+    rows, N = x.shape
+    T = (N + 2 * (win_len - win_inc) - win_len) // win_inc + 1
+    out = np.full((rows, 2 * (fft_len // 2 + 1), T), np.nan, np.float32)
+    check(lib().se_conv_stft_fwd_w(ptr(x), ptr(out), i64(rows), i64(N), ci(win_len), ci(win_inc), ci(fft_len), ci(wid), None))
+    return out
+
+
+def conv_istft_fwd_w(spec, out_len, win_len, win_inc, fft_len, wid):
+    rows, _, T = spec.shape
+    out = np.full((rows, out_len), np.nan, np.float32)
+    check(lib().se_conv_istft_fwd_w(ptr(spec), ptr(out), i64(rows), i64(T), i64(out_len), ci(win_len), ci(win_inc),
+                                    ci(fft_len), ci(wid), None))
+    return out
+
+
+def conv_istft_bwd_w(gy, T, win_len, win_inc, fft_len, wid):
+    rows, out_len = gy.shape
+    out = np.full((rows, 2 * (fft_len // 2 + 1), T), np.nan, np.float32)
+    check(lib().se_conv_istft_bwd_w(ptr(gy), ptr(out), i64(rows), i64(T), i64(out_len), ci(win_len), ci(win_inc),
+                                    ci(fft_len), ci(wid), None))
+    return out
+
+
+def polar_round_trip(spec):
+    rows, nf2, T = spec.shape
+    mags = np.full((rows, nf2 // 2, T), np.nan, np.float32)
+    phase = np.full_like(mags, np.nan)
+    check(lib().se_polar_from_planar(ptr(spec), ptr(mags), ptr(phase), i64(rows), i64(nf2 // 2), i64(T), None))
+    back = np.full_like(spec, np.nan)
+    check(lib().se_planar_from_polar(ptr(mags), ptr(phase), ptr(back), i64(rows), i64(nf2 // 2), i64(T), None))
+    return mags, phase, back
+
+
+def planar_from_polar_bwd(mags, phase, g):
+    rows, nf, T = mags.shape
+    gm, gp = np.full_like(mags, np.nan), np.full_like(mags, np.nan)
+    check(lib().se_planar_from_polar_bwd(ptr(mags), ptr(phase), ptr(g), ptr(gm), ptr(gp), i64(rows), i64(nf), i64(T), None))
+    return gm, gp
+
+
 def enhance_fwd(x, mask, n, hop, win, mode, pre_tanh):
     rows, N = x.shape
     out = np.full((rows, N), np.nan, np.float32)

@@ -39,8 +39,28 @@ def test_unsupported_configs_raise_not_fallback():
         se.apply_mask(torch.randn(1, 1, 257, 33, 2), torch.randn(1, 1, 257, 33), "E")
     with pytest.raises(ValueError):
         se.apply_mask(torch.randn(1, 1, 257, 33, 2), torch.randn(1, 1, 257, 33, 2), "Z")
-    with pytest.raises(NotImplementedError):
-        se.ConvSTFT(400, 100, 512, "hamming")
+
+
+def test_dccrn_modules_load_a_reference_state_dict_strictly():
+    """Same registered buffers as the reference's ConvSTFT / ConviSTFT (src/model/dccrn.py:681,714,720-721), built like
+    `init_kernels` (:649-666) builds them, for every window type scipy knows -- including the constructors' default
+    'hamming': a reference checkpoint loads with strict=True.  The fixture values are the REAL reference's buffers
+    (tests/golden/conv_*.npz hold hann; the hamming ones are rebuilt here with the reference's own formula)."""
+    import numpy as np
+    from scipy.signal import get_window
+    st, ist = se.ConvSTFT(400, 100, 512), se.ConviSTFT(400, 100, 512)            # defaults: win_type='hamming'
+    assert set(st.state_dict()) == {"weight"} and set(ist.state_dict()) == {"weight", "window", "enframe"}
+    assert tuple(st.weight.shape) == (514, 1, 400) and tuple(ist.weight.shape) == (514, 1, 400)
+    assert tuple(ist.window.shape) == (1, 400, 1) and tuple(ist.enframe.shape) == (400, 1, 400)
+    w = get_window("hamming", 400, fftbins=True)
+    basis = np.fft.rfft(np.eye(512))[:400]
+    kernel = np.concatenate([np.real(basis), np.imag(basis)], 1).T
+    assert np.array_equal(st.weight.numpy(), (kernel * w)[:, None, :].astype(np.float32))
+    assert np.array_equal(ist.weight.numpy(), (np.linalg.pinv(kernel).T * w)[:, None, :].astype(np.float32))
+    fresh = se.ConviSTFT(400, 100, 512, win_type="hann")
+    fresh.load_state_dict(ist.state_dict(), strict=True)
+    for wt in ("hann", "hamming", "blackman", None, "None"):
+        se.ConvSTFT(400, 100, 512, wt)
 
 
 def test_modules_keep_reference_attributes():

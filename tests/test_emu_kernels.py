@@ -465,3 +465,42 @@ def test_emu_evaluate_fused_stats_segments_stitch_match_reference_golden(tag):
                                                              segment=nfeat / 16000.0))
     want = oref.evaluate_ref(torch.from_numpy(mix), lambda s: s * torch.from_numpy(f), conf).numpy()
     assert rel(out2.reshape(mix.shape), want) < 1e-5
+
+
+@pytest.mark.parametrize("win_type", ["hamming", "blackman", None])
+def test_emu_dccrn_transforms_with_any_scipy_window(win_type):
+    """ConvSTFT / ConviSTFT with the window types the reference accepts (src/model/dccrn.py:651-655; 'hamming' is the
+    constructors' default): values registered once, same kernels; against the oracle's dense conv / conv_transpose."""
+    from scipy.signal import get_window
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 3000)).astype(np.float32)
+    w = np.ones(400) if win_type is None else get_window(win_type, 400, fftbins=True)
+    wid = E.register_window(w)
+    assert E.register_window(w) == wid                                   # identical values share an id
+    spec = E.conv_stft_fwd_w(x, 400, 100, 512, wid)
+    want = oref.conv_stft_ref(torch.from_numpy(x), 400, 100, 512, win_type).numpy()
+    assert rel(spec, want) < 1e-5
+    y = E.conv_istft_fwd_w(spec, 3000, 400, 100, 512, wid)
+    ywant = oref.conv_istft_ref(torch.from_numpy(spec), 400, 100, 512, win_type, length=3000).numpy()[:, 0]
+    assert rel(y, ywant) < 1e-5
+    gy = rng.standard_normal(y.shape).astype(np.float32)
+    st = torch.from_numpy(spec).requires_grad_(True)
+    (gwant,) = torch.autograd.grad(oref.conv_istft_ref(st, 400, 100, 512, win_type, length=3000), st, torch.from_numpy(gy)[:, None])
+    assert rel(E.conv_istft_bwd_w(gy, spec.shape[-1], 400, 100, 512, wid), gwant.numpy()) < 1e-5
+
+
+def test_emu_dccrn_polar_feature_ops():
+    """ConvSTFT(feature_type='real') epilogue and ConviSTFT(inputs, phase) prologue as single launches, and the
+    prologue's gradient, against torch."""
+    rng = np.random.default_rng(6)
+    spec = rng.standard_normal((2, 514, 9)).astype(np.float32)
+    mags, phase, back = E.polar_round_trip(spec)
+    t = torch.from_numpy(spec)
+    assert rel(mags, torch.sqrt(t[:, :257] ** 2 + t[:, 257:] ** 2).numpy()) < 1e-6
+    assert rel(phase, torch.atan2(t[:, 257:], t[:, :257]).numpy()) < 1e-6
+    assert rel(back, spec) < 1e-6
+    g = rng.standard_normal(spec.shape).astype(np.float32)
+    m, p = torch.from_numpy(mags).requires_grad_(True), torch.from_numpy(phase).requires_grad_(True)
+    gm, gp = torch.autograd.grad(torch.cat([m * torch.cos(p), m * torch.sin(p)], 1), (m, p), torch.from_numpy(g))
+    got_m, got_p = E.planar_from_polar_bwd(mags, phase, g)
+    assert rel(got_m, gm.numpy()) < 1e-6 and rel(got_p, gp.numpy()) < 1e-6

@@ -1,6 +1,7 @@
 """Parity of the CUDA path (through the C-ABI) against the oracle and the reference's golden
 vectors.  Tolerances are BASELINE.json's: spectra / waveforms 1e-4 relative, loss / gradients
 1e-3 relative (relative = max |err| / max |ref|)."""
+import math
 import types
 
 import numpy as np
@@ -427,6 +428,73 @@ def test_conv_polar_golden(se):
     ist = se.ConviSTFT(400, 100, 512, None, "hann", "real")
     y = ist(torch.from_numpy(g["mags"]).cuda(), torch.from_numpy(g["phase"]).cuda())
     assert rel(y, torch.from_numpy(g["y"])) < TOL_SPEC
+
+
+@pytest.mark.parametrize("win_type", ["hamming", "blackman", None])
+def test_dccrn_modules_with_any_scipy_window(se, oref, win_type):
+    """The reference's constructors default to win_type='hamming' and take any scipy window (src/model/dccrn.py:651-655,
+    671,705): analysis, synthesis, autograd and the fused mask tail against the oracle's dense conv path."""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(3, 1, 6000, generator=g)
+    st = se.ConvSTFT(400, 100, 512, win_type, "complex").cuda()
+    ist = se.ConviSTFT(400, 100, 512, 6000, win_type, "complex").cuda()
+    spec = st(x.cuda())
+    want = oref.conv_stft_ref(x, 400, 100, 512, win_type)
+    assert rel(spec, want) < TOL_SPEC
+    s = want.clone().requires_grad_(True)
+    yw = oref.conv_istft_ref(s, 400, 100, 512, win_type, length=6000)
+    gy = torch.randn(yw.shape, generator=g)
+    (gw,) = torch.autograd.grad(yw, s, gy)
+    s2 = want.cuda().requires_grad_(True)
+    y = ist(s2)
+    (gs,) = torch.autograd.grad(y, s2, gy.cuda())
+    assert rel(y, yw) < TOL_SPEC and rel(gs, gw) < TOL_GRAD
+    mre, mim = torch.randn(3, 257, spec.shape[-1], generator=g), torch.randn(3, 257, spec.shape[-1], generator=g)
+    masked = oref.mask_apply_ref(torch.stack([want[:, :257], want[:, 257:]], -1), torch.stack([mre, mim], -1), "C")
+    yw2 = oref.conv_istft_ref(torch.cat([masked[..., 0], masked[..., 1]], 1), 400, 100, 512, win_type, length=6000)
+    assert rel(ist.forward_masked(spec, mre.cuda(), mim.cuda(), "C"), yw2) < TOL_SPEC
+    # a reference state dict (same buffer names and shapes) loads strictly
+    ist.load_state_dict({k: v.clone() for k, v in ist.state_dict().items()}, strict=True)
+
+
+def test_dccrn_real_feature_path_is_fused_and_differentiable(se, oref):
+    """feature_type='real': ConvSTFT returns (mags, phase) (dccrn.py:696-701) and ConviSTFT takes (mags, phase) (:729-732);
+    one launch each, gradient to both."""
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 5000, generator=g)
+    st = se.ConvSTFT(400, 100, 512, "hann", "real").cuda()
+    ist = se.ConviSTFT(400, 100, 512, 5000, "hann", "real").cuda()
+    mags, phase = st(x.cuda())
+    wm, wp = oref.conv_stft_ref(x, 400, 100, 512, "hann", "real")
+    assert rel(mags, wm) < TOL_SPEC
+    assert float(torch.remainder(phase.cpu() - wp + math.pi, 2 * math.pi).sub(math.pi).abs().mul(wm > 1e-3).max()) < 1e-4
+    m1, p1 = wm.clone().requires_grad_(True), wp.clone().requires_grad_(True)
+    yw = oref.conv_istft_ref(m1, 400, 100, 512, "hann", length=5000, phase=p1)
+    gy = torch.randn(yw.shape, generator=g)
+    gmw, gpw = torch.autograd.grad(yw, (m1, p1), gy)
+    m2, p2 = wm.cuda().requires_grad_(True), wp.cuda().requires_grad_(True)
+    y = ist(m2, p2)
+    gm, gp = torch.autograd.grad(y, (m2, p2), gy.cuda())
+    assert rel(y, yw) < TOL_SPEC and rel(gm, gmw) < TOL_GRAD and rel(gp, gpw) < TOL_GRAD
+
+
+def test_float64_inputs_are_accepted_like_the_reference(se, oref):
+    """The reference passes dtype=tensor.dtype (src/evaluate.py:113,147) and works in float64; here float64 inputs are
+    computed in fp32 and returned as float64: tolerance 1e-5 relative against the float64 oracle."""
+    c = cfg(512, 128, 512)
+    g = torch.Generator().manual_seed(33)
+    x = torch.randn(2, 1, 8000, generator=g, dtype=torch.float64)
+    spec = se.stft_custom(x.cuda(), c)
+    assert spec.dtype == torch.float64
+    want = oref.stft_custom_ref(x, c)
+    assert rel(spec, want) < 1e-5
+    y = se.istft_custom(spec, 8000, c)
+    assert y.dtype == torch.float64 and rel(y, x) < 1e-5
+    xg = x.cuda().requires_grad_(True)
+    (gx,) = torch.autograd.grad(se.stft_custom(xg, c).square().sum(), xg)
+    xr = x.clone().requires_grad_(True)
+    (gr,) = torch.autograd.grad(oref.stft_custom_ref(xr, c).square().sum(), xr)
+    assert gx.dtype == torch.float64 and rel(gx, gr) < 1e-5
 
 
 @pytest.mark.parametrize("mode", ["E", "C", "R"])
