@@ -659,6 +659,33 @@ def run_ours(args):
                             "alg_bytes": bytes_row * rows, "gbs": round(bytes_row * rows / us * 1e-3, 1),
                             "tflops_fp32": round(flops_row * rows / us * 1e-6, 2)})
 
+    # ---- what the reference-facing API adds on top of the raw C-ABI launch (no-grad calls, same shapes)
+    api_overhead = None
+    if rank == 0 and not args.no_breakdown:
+        import types as _types
+        cfg0 = _types.SimpleNamespace(n_fft=N_FFT, hop_length=HOP, win_length=WIN, center=True)
+        x5 = sets[0][0].reshape(rows, 1, N)
+        with torch.no_grad():
+            spec5 = se.stft_custom(x5, cfg0)
+
+            def t_api(fn, reps=50):
+                for _ in range(5):
+                    fn()
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(reps):
+                    fn()
+                b.record()
+                torch.cuda.synchronize(dev)
+                return a.elapsed_time(b) * 1e3 / reps
+            raw_us = {k["name"]: k["us"] for k in kernels}
+            api_overhead = {"stft_custom_us": round(t_api(lambda: se.stft_custom(x5, cfg0)), 2), "se_stft_fwd_us": raw_us.get("stft_fwd"),
+                            "istft_custom_us": round(t_api(lambda: se.istft_custom(spec5, N, cfg0)), 2), "se_istft_fwd_us": raw_us.get("istft_fwd"),
+                            "note": "public API (C++ extension op: checks, output allocation, current stream) vs the raw C-ABI launch with "
+                                    "preallocated outputs, back-to-back calls, CUDA events"}
+        del spec5
+
     # the sampler ran through the timed region, the alternative composition and the per-kernel loops (all under load)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -900,7 +927,7 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "rounds_ms_per_step": [round(v, 5) for v in rounds_ms], "timing": "median of rounds",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, world, exchange),
-        "clocks": clocks, "e2e": e2e, "configs": configs, "incumbent": incumbent, "sharded_loss_check": shard_check, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
+        "clocks": clocks, "e2e": e2e, "configs": configs, "incumbent": incumbent, "sharded_loss_check": shard_check, "api_overhead": api_overhead, "gpu_launches": n_launch * args.steps, "launches_per_step": n_launch,
         "composition": comp, "alt_compositions": alts,
         "loss": loss_val, "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
     }))

@@ -58,6 +58,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps if os.path.exists(p))
 
 
+ALT_LIB_PATH = os.path.join(_PKG, "libse_alt_tc.so")      # measured alternative (tensor-core DFT-as-GEMM); never loaded by the package
+CSRC_ALT = os.path.join(_PKG, "csrc_alt")
+
+
+def build_alt(force: bool = False) -> str:
+    """Compile csrc_alt/*.cu (the measured tensor-core alternative of profiles/r02_notes.md (c), used only by
+    tools/tc_dft_bench.py) for sm_100a so that every CUDA source in the tree is covered by the build check."""
+    srcs = sorted(os.path.join(CSRC_ALT, f) for f in os.listdir(CSRC_ALT) if f.endswith(".cu"))
+    if not force and os.path.exists(ALT_LIB_PATH) and all(os.path.getmtime(p) <= os.path.getmtime(ALT_LIB_PATH) for p in srcs):
+        return ALT_LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    res = subprocess.run([nvcc] + NVCC_FLAGS + ["-o", ALT_LIB_PATH] + srcs, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc (csrc_alt) failed:\n" + res.stdout + res.stderr)
+    return ALT_LIB_PATH
+
+
 def _torch_sources():
     return sorted(os.path.join(CSRC_TORCH, f) for f in os.listdir(CSRC_TORCH) if f.endswith(".cpp"))
 
@@ -94,6 +111,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     link the in-tree libse_b200.so."""
     if not (force or needs_build()):
         build_torch_ext(force=False)
+        build_alt(force=False)
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -119,6 +137,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(os.path.join(BUILD_DIR, "ptxas.log"), "w") as f:
             f.write(log)
     build_torch_ext(force=True)
+    build_alt(force=force)
     return LIB_PATH
 
 

@@ -4,10 +4,10 @@
 using namespace se;
 
 // planning happens here, where the geometry (frames per group, CTAs per SM) is known
-template <class G, int LMODE>
+template <class G, int LMODE, bool NORM = false>
 static cudaError_t run_analysis(AnaArgs a, int64_t rows, cudaStream_t st) {
     plan_analysis(rows, a.nframe, a.gpc, a.nchunks, G::FR);
-    return launch(k_analysis<G, LMODE, false>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, st, a);
+    return launch(k_analysis<G, LMODE, false, NORM>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, st, a);
 }
 template <class G, int EMODE>
 static cudaError_t run_synthesis(SynArgs a, int64_t rows, cudaStream_t st) {
@@ -160,7 +160,7 @@ int se_stft_segments_norm_fwd(const float* x, float* spec, const float* stats, i
     a.norm = reinterpret_cast<const float4*>(stats); a.norm_div = (int)stats_div; a.norm_c = (int)stats_c;
     a.nframe = (int)(1 + nsample / hop); a.pad = 0; a.edge_scale = 1.0f;
     cudaError_t e;
-    if (stats) SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT>(a, rows, (cudaStream_t)stream)));   // scalar engine: it has the normalising fill
+    if (stats) SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LOAD_REFLECT, true>(a, rows, (cudaStream_t)stream)));   // scalar engine: it has the normalising fill
     else e = dispatch_analysis<LOAD_REFLECT>(a, rows, n_fft, hop, (cudaStream_t)stream);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_segments_fwd launch");
 }

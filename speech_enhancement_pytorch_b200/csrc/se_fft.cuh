@@ -107,14 +107,14 @@ __device__ __forceinline__ void dftR(float2* a) {
 }
 
 // ------------------------------------------------------------------ geometry
-template <int N_, int HOP_, int NT_, int FR_ = 16>
+template <int N_, int HOP_, int NT_, int FR_ = 16, int MINB_ = 0>
 struct Geo {
     static constexpr int N = N_, HOP = HOP_, NT = NT_;
     static constexpr int M = N / 2;            // complex points
     static constexpr int R1 = M / 64;          // radix of the time-side pass (4, 8, 16)
     static constexpr int FR = FR_;             // frames per group (= lanes per butterfly): 16, or 8 to halve the working set
     static constexpr int NU = NT / FR;         // butterfly units working in parallel per frame
-    static constexpr int MINB = NT <= 128 ? 4 : (NT <= 256 ? 2 : 1);   // CTAs per SM the register budget is sized for
+    static constexpr int MINB = MINB_ > 0 ? MINB_ : (NT <= 128 ? 4 : (NT <= 256 ? 2 : 1));   // CTAs per SM the register budget is sized for
     static constexpr int TA = 64 / NU;         // pass-A tasks per thread   (64 radix-R1 butterflies)
     static constexpr int TB = 8 * R1 / NU;     // pass-B tasks per thread   (8*R1 radix-8 butterflies)
     static constexpr int TC = 4 * R1 / NU;     // pass-C paired tasks per thread (M/16 pairs)

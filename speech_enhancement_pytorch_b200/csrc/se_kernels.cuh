@@ -87,7 +87,9 @@ __device__ __forceinline__ float inv_env_at(const Tables& tb, int T, int i) {
 // All global loads of a thread are issued back to back into registers before the first store, so a
 // fill costs ONE memory round trip instead of one per loop iteration (ncu: the store that waited on
 // the load held 90 % of the long-scoreboard samples before this change).
-template <class G, int LMODE>
+// NORM (evaluate()'s z-score) is a template switch: with the affine map compiled into every instance the plain STFT
+// lost 15 % (28.7 -> 33.1 us at cfg2: different schedule, the loads no longer batch as well)
+template <class G, int LMODE, bool NORM = false>
 __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const float* __restrict__ src,
                                            int p0, const AnaArgs& a, int tid, int nvalid = 0x7fffffff,
                                            float nm_mean = 0.f, float nm_inv = 1.f) {
@@ -120,8 +122,10 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
             if (slot >= SLOTS) continue;
             const int i = p0 + 2 * slot;
             if (LMODE == LOAD_REFLECT) {
-                v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i, nvalid, nm_mean, nm_inv),
-                                   sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1, nvalid, nm_mean, nm_inv));
+                if (NORM) v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i, nvalid, nm_mean, nm_inv),
+                                             sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1, nvalid, nm_mean, nm_inv));
+                else v[k] = make_float2(sample_reflect(src, G::N / 2, a.nsample, G::N, i, nvalid),
+                                        sample_reflect(src, G::N / 2, a.nsample, G::N, i + 1, nvalid));
             } else if (LMODE == LOAD_ZEROPAD) {
                 const int j = i - a.pad;
                 v[k] = make_float2((j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f,
@@ -139,7 +143,7 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
         if (slot >= SLOTS) continue;
         const int rel = 2 * slot;
         float2 w = v[k];
-        if (LMODE == LOAD_REFLECT && interior) w = make_float2((w.x - nm_mean) * nm_inv, (w.y - nm_mean) * nm_inv);
+        if (NORM && LMODE == LOAD_REFLECT && interior) w = make_float2((w.x - nm_mean) * nm_inv, (w.y - nm_mean) * nm_inv);
         if (LMODE == LOAD_ENV) {      // gy / envelope (zero where the envelope is empty)
             const int i = p0 + rel;
             w.x *= inv_env_at<G>(a.tb, a.nframe, i);
@@ -478,7 +482,7 @@ template <class G> struct Smem {
 
 // ================================================================== kernels
 // wave-like rows -> spectrum.  LMODE picks the padded-signal definition, PLANAR the layout.
-template <class G, int LMODE, bool PLANAR>
+template <class G, int LMODE, bool PLANAR, bool NORM = false>
 __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     SE_SMEM_DECL;
     float2* zb = reinterpret_cast<float2*>(se_smem);
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
         nvalid = left < 0 ? 0 : (left < a.nsample ? (int)left : a.nsample);
     }
     float nm_mean = 0.f, nm_inv = 1.f;
-    if (a.norm) {
+    if (NORM && a.norm) {
         const float4 st = __ldg(a.norm + (clip / a.norm_div) * a.norm_c + clip % a.norm_c);
         nm_mean = st.x;
         nm_inv = st.y;
@@ -504,7 +508,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
     for (int g = 0; g < a.gpc; ++g) {
         const int f_base = (chunk * a.gpc + g) * G::FR;
         if (f_base >= a.nframe) break;
-        fill_stage<G, LMODE>(stage, src, f_base * G::HOP, a, tid, nvalid, nm_mean, nm_inv);
+        fill_stage<G, LMODE, NORM>(stage, src, f_base * G::HOP, a, tid, nvalid, nm_mean, nm_inv);
         __syncthreads();
         analysis_passes<G>(stage, tb, zb, unit, fr);
         const int t = f_base + fr;
