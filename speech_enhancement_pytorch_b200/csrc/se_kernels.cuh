@@ -153,6 +153,32 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
     }
 }
 
+// Asynchronous variant for interior spans of the reflect-padded signal: issues the whole fill as cp.async copies and
+// returns true; the caller waits (se_cp_async_wait_all + barrier) right before pass A reads the stage.  Returns false
+// -- nothing issued -- when the span touches a signal edge or the source is not 8-byte aligned (the synchronous
+// fill_stage handles those).  The stage is only read in pass A, so the fill of the NEXT transform can be issued as soon
+// as pass A's barrier has passed and lands while passes B and C run (round 1 measured the exposed fill latency at
+// 12 % of the loss forward: profiles/r01_notes.md (e)).
+template <class G>
+__device__ __forceinline__ bool fill_stage_async(float* __restrict__ stage, const float* __restrict__ src, int p0, int nsample,
+                                                 int tid) {
+    constexpr int SLOTS = G::SROWS * G::HOP / 2;
+    constexpr int K = (SLOTS + G::NT - 1) / G::NT;
+    const int base = p0 - G::N / 2;
+    if (base < 0 || base + 2 * SLOTS > nsample || (reinterpret_cast<uintptr_t>(src + base) & 7) != 0) return false;
+    const float2* s2 = reinterpret_cast<const float2*>(src + base);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int slot = tid + k * G::NT;
+        if (slot < SLOTS) {
+            const int rel = 2 * slot;
+            se_cp_async8(stage + (rel / G::HOP) * G::SROW + rel % G::HOP, s2 + slot);
+        }
+    }
+    se_cp_async_commit();
+    return true;
+}
+
 // ------------------------------------------------------------------ magnitude features
 // NN input features computed from the spectrum, quirks of the reference kept:
 //   0 power     |re^2 + im^2|      src/model/unet.py:40
@@ -727,6 +753,7 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
     AnaArgs la;
     la.tb = a.tb; la.nsample = a.nsample; la.nframe = a.nframe; la.in_len = a.nsample; la.pad = 0;
     float s_d2 = 0.f, s_b2 = 0.f, s_lm = 0.f;
+    bool prefetched = false;
     for (int g = 0; g < a.gpc; ++g) {
         const int f_base = (chunk * a.gpc + g) * G::FR;
         if (f_base >= a.nframe) break;
@@ -734,9 +761,21 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_fwd(const LossArgs a) {
         float pb[G::TC][17];
 #pragma unroll 1
         for (int sig = 0; sig < 2; ++sig) {              // 0: reference magnitudes, 1: estimate + statistics
-            fill_stage<G, LOAD_REFLECT>(stage, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
+            if (prefetched) se_cp_async_wait_all();      // this transform's fill was issued during the previous one
+            else fill_stage<G, LOAD_REFLECT>(stage, (sig ? a.est : a.ref) + (size_t)row * a.nsample, f_base * G::HOP, la, tid);
             __syncthreads();
-            analysis_passes<G>(stage, tb, zb, unit, fr);
+            passA_fwd<G>(stage, tb.win, tb.tw, zb, unit, fr);
+            __syncthreads();
+            // the stage is free from here on: start the NEXT transform's fill (the estimate of this group, or the
+            // reference of the next group) so that it lands while passes B and C run
+            {
+                const int nf_base = sig ? f_base + G::FR : f_base;
+                const bool more = sig == 0 || (g + 1 < a.gpc && nf_base < a.nframe);
+                prefetched = more && fill_stage_async<G>(stage, (sig ? a.ref : a.est) + (size_t)row * a.nsample, nf_base * G::HOP,
+                                                         a.nsample, tid);
+            }
+            passB_fwd<G>(tb.tw, zb, unit, fr);
+            __syncthreads();
 #pragma unroll
             for (int i = 0; i < G::TC; ++i) {
                 const int p = unit + i * G::NU;

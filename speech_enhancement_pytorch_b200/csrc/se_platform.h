@@ -71,6 +71,27 @@ __device__ __forceinline__ float se_log2(float x) {
 #endif
 }
 
+// cp.async (LDGSTS): 8-byte global -> shared copies that bypass registers; the stage rows are 8-byte aligned (their pitch
+// is == 2 words mod 32), so this is the widest form they take.  commit + wait bracket a fill.
+__device__ __forceinline__ void se_cp_async8(void* smem_dst, const void* gmem_src) {
+#ifdef SE_EMULATE
+    *reinterpret_cast<float2*>(smem_dst) = *reinterpret_cast<const float2*>(gmem_src);
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void se_cp_async_commit() {
+#ifndef SE_EMULATE
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void se_cp_async_wait_all() {
+#ifndef SE_EMULATE
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // A product that must stay a rounded product: without this the compiler contracts `x*y - u*v` into an FMA whose
 // inner product is unrounded, so the difference of two bit-identical products comes out as their rounding error, not 0.
 __device__ __forceinline__ float se_mul_rn(float a, float b) {
