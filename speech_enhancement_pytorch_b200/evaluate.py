@@ -39,6 +39,9 @@ def stft_custom_with_feature(tensor, config, kind):
         raise ValueError(f"unknown feature kind {kind!r}")
     n_fft, hop, win = _cfg(config)
     ops._check_cfg(n_fft, hop, win)
+    if torch.is_grad_enabled() and tensor.requires_grad:
+        # torch.stft is differentiable wrt the waveform; this fused variant has no adjoint wired (use stft_custom)
+        raise NotImplementedError("stft_custom_with_feature: gradient wrt the input waveform is not built")
     lead, nsample = tuple(tensor.shape[:-1]), tensor.shape[-1]
     x = ops._as_f32(tensor).reshape(-1, nsample).contiguous()
     nv.require_cuda_f32(x)
@@ -101,6 +104,8 @@ def segment_stft(wave, num_feature, stride, config, stats=None):
     ops._check_cfg(n_fft, hop, win)
     if wave.dim() != 3:
         raise ValueError("segment_stft expects [B,C,L]")
+    if torch.is_grad_enabled() and wave.requires_grad:
+        raise NotImplementedError("segment_stft: gradient wrt the input waveform is not built (evaluate() runs under no_grad)")
     nb, nc, length = wave.shape
     if length < num_feature:
         raise AssertionError("the length of data is too short comparing the number of features...")

@@ -31,6 +31,9 @@ def collate_pad(batch, segment_length, drop_last=True, out=None):
         mix = torch.zeros(total, nch, segment_length, dtype=batch[0][0].dtype)
         src = torch.zeros(total, nspk, nch, segment_length, dtype=batch[0][1].dtype)
     else:
+        if total > out[0].shape[0] or total > out[1].shape[0]:
+            raise ValueError(f"batch has {total} segments but the staging buffers hold {min(out[0].shape[0], out[1].shape[0])} "
+                             "(raise max_segments)")
         mix, src = out[0][:total], out[1][:total]
         mix.zero_()
         src.zero_()
@@ -57,8 +60,11 @@ class PinnedFeeder:
             ...
 
     `loader` yields lists of (mixture [C,L], sources [S,C,L], ...) items (a DataLoader with
-    `collate_fn=lambda b: b`).  The yielded tensors are views of the staging slots: they are valid until
-    the next-but-one iteration (the slot is recycled after the consumer's stream has passed it).
+    `collate_fn=lambda b: b`).  The yielded tensors are views of the device staging slots.  Lifetime: a batch is valid
+    until the NEXT batch is requested, for work queued on the current stream up to that point -- requesting batch i+1
+    records the consumer's progress and immediately queues the upload of batch i+2 into batch i's slot behind it.  Work
+    on batch i that is queued later, or on another stream without an event dependency, races with that upload: clone
+    what must live longer.  A batch with more than `max_segments` segments raises ValueError.
     """
 
     def __init__(self, loader, segment_length, device, max_segments, channels=1, speakers=1, drop_last=True):

@@ -51,3 +51,10 @@ def test_collate_pad_matches_reference_run_golden(tag, drop):
     assert np.array_equal(mix.numpy(), gd[f"batch_mix_{tag}"])
     assert np.array_equal(src.numpy(), gd[f"batch_src_{tag}"])
     assert list(nsegs) == list(gd[f"index_{tag}"])
+
+
+def test_collate_pad_rejects_batches_larger_than_the_staging_buffers():
+    batch = make_batch([9000, 9000])
+    out = (torch.empty(3, 2, 4000), torch.empty(3, 1, 2, 4000))
+    with pytest.raises(ValueError, match="max_segments"):
+        feeder.collate_pad(batch, 4000, True, out=out)
