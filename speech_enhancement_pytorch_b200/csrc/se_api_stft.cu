@@ -64,10 +64,25 @@ static bool run_synthesis2(SynArgs a, int64_t rows, cudaStream_t st, cudaError_t
         else { constexpr int N2 = 2048, HOP2 = 1024, NT2 = 512; CALL; }                                 \
     } while (0)
 
+// ---- two-pass engine (se_fft3.cuh): n_fft 512 / 1024 at hop n/4
+template <class G3, int LMODE>
+static cudaError_t run_analysis3(AnaArgs a, int64_t rows, cudaStream_t st) {
+    plan_analysis(rows, a.nframe, a.gpc, a.nchunks, G3::FR);
+    return launch(k_analysis3<G3, LMODE>, (unsigned)(rows * a.nchunks), G3::NT, Smem<typename G3::Base>::ANALYSIS, st, a);
+}
+template <class G3, int EMODE>
+static cudaError_t run_synthesis3(SynArgs a, int64_t rows, cudaStream_t st) {
+    a.nchunks = plan_synthesis(rows, a.b_hi - a.b_lo, G3::OLA, G3::MINB, G3::FR);
+    return launch(k_synthesis3<G3, EMODE>, (unsigned)(rows * a.nchunks), G3::NT,
+                  EMODE == EMIT_ADJ ? Smem<typename G3::Base>::SYNTH_ADJ : Smem<typename G3::Base>::SYNTH_ISTFT, st, a);
+}
+
 template <int LMODE>
 static cudaError_t dispatch_analysis(const AnaArgs& a, int64_t rows, int n_fft, int hop, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     bool done = false;
+    if (engine_version() == 3 && !a.norm && n_fft == 1024 && hop == 256) return run_analysis3<Geo3<1024, 256, 256>, LMODE>(a, rows, st);
+    if (engine_version() == 3 && !a.norm && n_fft == 512 && hop == 128) return run_analysis3<Geo3<512, 128, 128>, LMODE>(a, rows, st);
     if (engine_version() == 2) SE_DISPATCH_GEO2(n_fft, hop, (done = run_analysis2<N2, HOP2, NT2, LMODE>(a, rows, st, e)));
     if (!done) SE_DISPATCH_GEO(n_fft, hop, (e = run_analysis<G, LMODE>(a, rows, st)));
     return e;
@@ -76,6 +91,8 @@ template <int EMODE>
 static cudaError_t dispatch_synthesis(const SynArgs& a, int64_t rows, int n_fft, int hop, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     bool done = false;
+    if (engine_version() == 3 && n_fft == 1024 && hop == 256) return run_synthesis3<Geo3<1024, 256, 256>, EMODE>(a, rows, st);
+    if (engine_version() == 3 && n_fft == 512 && hop == 128) return run_synthesis3<Geo3<512, 128, 128>, EMODE>(a, rows, st);
     if (engine_version() == 2) SE_DISPATCH_GEO2(n_fft, hop, (done = run_synthesis2<N2, HOP2, NT2, EMODE>(a, rows, st, e)));
     if (!done) SE_DISPATCH_GEO(n_fft, hop, (e = run_synthesis<G, EMODE>(a, rows, st)));
     return e;

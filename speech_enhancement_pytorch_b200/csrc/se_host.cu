@@ -157,7 +157,7 @@ static bool envelope_ok_uncached(int n, int hop, int win_len, bool front, int64_
 }
 
 int engine_version() {
-    auto read = [] { const char* e = std::getenv("SE_ENGINE"); return (e && e[0] == '2') ? 2 : 1; };
+    auto read = [] { const char* e = std::getenv("SE_ENGINE"); return (e && e[0] == '2') ? 2 : ((e && e[0] == '3') ? 3 : 1); };
 #ifdef SE_EMULATE
     return read();           // tests flip it between calls
 #else
@@ -182,7 +182,8 @@ static int g_target_ctas = 148 * 8;
 
 void plan_analysis(int64_t rows, int64_t T, int& gpc, int& nchunks, int frames_per_group) {
     const int64_t ng = (T + frames_per_group - 1) / frames_per_group;
-    int64_t g = (rows * ng) / g_target_ctas;
+    static const int target = [] { const char* e = std::getenv("SE_TARGET_CTAS"); return e ? std::atoi(e) : 0; }();
+    int64_t g = (rows * ng) / (target > 0 ? target : g_target_ctas);
     g = g < 1 ? 1 : (g > 8 ? 8 : g);
     gpc = (int)g;
     nchunks = (int)((ng + g - 1) / g);

@@ -2,6 +2,7 @@
 #pragma once
 #include "../../include/se_b200.h"
 #include "se_kernels2.cuh"
+#include "se_kernels3.cuh"
 
 #include <string>
 

@@ -504,3 +504,24 @@ def test_emu_dccrn_polar_feature_ops():
     gm, gp = torch.autograd.grad(torch.cat([m * torch.cos(p), m * torch.sin(p)], 1), (m, p), torch.from_numpy(g))
     got_m, got_p = E.planar_from_polar_bwd(mags, phase, g)
     assert rel(got_m, gm.numpy()) < 1e-6 and rel(got_p, gp.numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("n,hop,N", [(512, 128, 3001), (1024, 256, 6100)])
+def test_emu_two_pass_engine_matches_the_default_engine(n, hop, N, monkeypatch):
+    """SE_ENGINE=3 (csrc/se_fft3.cuh: radix-R1 x radix-16, one intermediate shared-memory round trip) against the
+    three-pass engine and the float64 oracle: STFT, iSTFT with a short length, both adjoints."""
+    rng = np.random.default_rng(n + N)
+    x = rng.standard_normal((3, N)).astype(np.float32)
+    out = {}
+    for eng in ("1", "3"):
+        monkeypatch.setenv("SE_ENGINE", eng)
+        spec = E.stft_fwd(x, n, hop, n, 1.0 / n)
+        y = E.istft_fwd(spec, N - 77, n, hop, n, float(n))
+        gx = E.stft_bwd(spec, N, n, hop, n, 1.0 / n)
+        gs = E.istft_bwd(y, spec.shape[2], n, hop, n, float(n))
+        assert not any(np.isnan(v).any() for v in (spec, y, gx, gs))
+        out[eng] = (spec, y, gx, gs)
+    want = o64.stft(x.astype(np.float64), n, hop, n)                  # scaled by 1 / win_length like stft_custom
+    assert rel(c2(out["3"][0]), want) < 1e-6
+    for a, b in zip(out["3"], out["1"]):
+        assert rel(a, b) < 2e-6
