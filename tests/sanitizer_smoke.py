@@ -67,7 +67,24 @@ def main():
     cfg = types.SimpleNamespace(dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
                                 model=types.SimpleNamespace(name="dnn", segment=0.256, n_fft=512, hop_length=128,
                                                             win_length=512, center=True))
-    se.evaluate(torch.randn(1, 2, 9000), None, dev, cfg)
+    se.evaluate(torch.randn(1, 2, 9000), None, dev, cfg)               # row_stats -> segment STFT (z-score fill) -> stitching iSTFT
+    cfg.dset.norm = "none"
+    se.evaluate(torch.randn(2, 1, 5000), None, dev, cfg)
+    # round 2: 10-double exchange (row counts travel with the sums), DCCRN windows + polar ops, float64 inputs
+    sums10 = torch.rand(10, dtype=torch.float64, device=dev) + 1.0
+    nv.check(L.se_p2p_create(ctypes.byref(local), handle))
+    ptrs = (ctypes.c_void_p * 1)(local.value)
+    nv.check(L.se_mrstft_exchange_rows_value(sums10.data_ptr(), ptrs, 1, 0, 7000, loss.data_ptr(), nv.stream_ptr(torch.device(dev, 0))))
+    nv.check(L.se_mrstft_loss_value_dev(sums10.data_ptr(), 7000, loss.data_ptr(), nv.stream_ptr(torch.device(dev, 0))))
+    torch.cuda.synchronize()
+    nv.check(L.se_p2p_destroy(local))
+    st2, ist2 = se.ConvSTFT(400, 100, 512), se.ConviSTFT(400, 100, 512, 3000)          # hamming, feature_type='real'
+    mags, phase = st2(torch.randn(2, 1, 3000, device=dev))
+    mags.requires_grad_(True)
+    phase.requires_grad_(True)
+    ist2(mags, phase).sum().backward()
+    c64 = types.SimpleNamespace(n_fft=512, hop_length=128, win_length=512, center=True)
+    se.istft_custom(se.stft_custom(torch.randn(1, 1, 3000, device=dev, dtype=torch.float64), c64), 3000, c64)
     torch.cuda.synchronize()
     print("sanitizer smoke done")
 
