@@ -84,6 +84,15 @@ int se_row_stats(const float* x, float* stats, int64_t rows, int64_t len, int64_
 int se_stft_segments_norm_fwd(const float* x, float* spec, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
                               int64_t nclip, int64_t clip_len, int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft,
                               int hop, int win_length, float scale, void* stream);
+/* se_stft_segments_shared_fwd: the same result as se_stft_segments_norm_fwd, computed with the frames that overlapping
+ * segments SHARE transformed once: segment s, frame t is frame s * (seg_stride / hop) + t of one clip-level transform
+ * whenever it does not touch the segment's reflect padding.  One clip-level launch into `scratch`
+ * (se_stft_segments_scratch_bytes; 0 = not applicable: seg_stride must be a multiple of hop), one launch for the groups
+ * of 16 frames that hold boundary frames (2 of T/16 per segment), one gather launch for the interior frames. */
+int64_t se_stft_segments_scratch_bytes(int64_t nseg, int64_t nclip, int64_t seg_stride, int64_t nsample, int n_fft, int hop);
+int se_stft_segments_shared_fwd(const float* x, float* spec, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
+                                int64_t nclip, int64_t clip_len, int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft,
+                                int hop, int win_length, float scale, void* scratch, void* stream);
 int se_istft_stitch_fwd(const float* spec, float* out, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
                         int64_t nclip, int64_t nframe, int64_t num_feature, int64_t stride, int64_t out_len, int64_t out_stride,
                         int n_fft, int hop, int win_length, float scale, void* stream);

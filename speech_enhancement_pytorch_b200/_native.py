@@ -22,7 +22,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = (
-    "se_version", "se_last_error", "se_stft_fwd", "se_stft_segments_fwd", "se_row_stats", "se_stft_segments_norm_fwd", "se_istft_stitch_fwd", "se_magnitude_feature", "se_stft_feature_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
+    "se_version", "se_last_error", "se_stft_fwd", "se_stft_segments_fwd", "se_row_stats", "se_stft_segments_norm_fwd", "se_istft_stitch_fwd",
+    "se_stft_segments_scratch_bytes", "se_stft_segments_shared_fwd", "se_magnitude_feature", "se_stft_feature_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
     "se_mask_fwd", "se_mask_bwd", "se_mrstft_workspace_bytes", "se_mrstft_loss_fwd",
     "se_mrstft_loss_value", "se_mrstft_loss_bwd", "se_spectral_loss_workspace_bytes", "se_spectral_loss_fwd",
     "se_spectral_loss_bwd", "se_sisnr_fwd", "se_sisnr_bwd", "se_psa_workspace_bytes", "se_psa_loss_fwd", "se_psa_loss_bwd", "se_enhance_fwd", "se_enhance_bwd",
@@ -166,6 +167,9 @@ def lib():
             L.se_stft_segments_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
             L.se_row_stats.argtypes = [_PTR, _PTR, _I64, _I64, _I64, _PTR]
             L.se_stft_segments_norm_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
+            L.se_stft_segments_scratch_bytes.restype = _I64
+            L.se_stft_segments_scratch_bytes.argtypes = [_I64, _I64, _I64, _I64, _INT, _INT]
+            L.se_stft_segments_shared_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR, _PTR]
             L.se_istft_stitch_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _INT, _INT, _INT, _F32, _PTR]
             L.se_magnitude_feature.argtypes = [_PTR, _PTR, _I64, _INT, _PTR]
             L.se_stft_feature_fwd.argtypes = [_PTR, _PTR, _PTR, _I64, _I64, _INT, _INT, _INT, _F32, _INT, _PTR]

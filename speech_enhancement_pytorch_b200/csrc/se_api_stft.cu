@@ -155,7 +155,7 @@ int se_stft_segments_fwd(const float* x, float* spec, int64_t nseg, int64_t ncli
 int se_row_stats(const float* x, float* stats, int64_t rows, int64_t len, int64_t row_stride, void* stream) {
     if (!x || !stats) return fail(SE_ERR_BAD_ARG, "null pointer");
     if (rows <= 0 || len <= 0 || row_stride < len) return fail(SE_ERR_BAD_ARG, "need rows > 0, len > 0, row_stride >= len");
-    cudaError_t e = launch(k_row_stats, (unsigned)rows, 256u, 0, (cudaStream_t)stream, x, reinterpret_cast<float4*>(stats), len, row_stride);
+    cudaError_t e = launch(k_row_stats, (unsigned)(rows * kStatsCluster), 1024u, 0, (cudaStream_t)stream, x, reinterpret_cast<float4*>(stats), len, row_stride);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_row_stats launch");
 }
 
@@ -253,6 +253,80 @@ int se_istft_stitch_fwd(const float* spec, float* out, const float* stats, int64
     cudaError_t e;
     SE_DISPATCH_GEO(n_fft, hop, (e = run_stitch<G>(a, s, (cudaStream_t)stream)));
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_istft_stitch_fwd launch");
+}
+
+// ---- evaluate(): segment STFT with the frames shared between overlapping segments computed once
+// scratch = the clip-level spectrum [nclip][F][Tg]; 0 when the shared path does not apply (seg_stride not a multiple of hop)
+static int64_t shared_frames(int64_t nseg, int64_t seg_stride, int64_t nsample, int n_fft, int hop, int64_t& t_lo, int64_t& t_hi) {
+    if (seg_stride % hop) return 0;
+    t_lo = (n_fft / 2 + hop - 1) / hop;                      // first frame that does not touch the left reflect padding
+    t_hi = (nsample - n_fft / 2) / hop;                      // last frame that does not touch the right one
+    if (t_hi < t_lo) return 0;
+    return (nseg - 1) * (seg_stride / hop) + t_hi + 1;       // clip-level frames needed
+}
+int64_t se_stft_segments_scratch_bytes(int64_t nseg, int64_t nclip, int64_t seg_stride, int64_t nsample, int n_fft, int hop) {
+    int64_t t_lo, t_hi;
+    const int64_t Tg = shared_frames(nseg, seg_stride, nsample, n_fft, hop, t_lo, t_hi);
+    return Tg <= 0 ? 0 : nclip * (int64_t)(n_fft / 2 + 1) * Tg * (int64_t)sizeof(float2);
+}
+
+int se_stft_segments_shared_fwd(const float* x, float* spec, const float* stats, int64_t stats_div, int64_t stats_c, int64_t nseg,
+                                int64_t nclip, int64_t clip_len, int64_t clip_stride, int64_t seg_stride, int64_t nsample, int n_fft,
+                                int hop, int win_length, float scale, void* scratch, void* stream) {
+    if (!x || !spec || !scratch) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (nseg <= 0 || nclip <= 0 || clip_len <= 0 || seg_stride <= 0 || clip_stride < clip_len) return fail(SE_ERR_BAD_ARG, "bad segment geometry");
+    if (stats && (stats_div <= 0 || stats_c <= 0)) return fail(SE_ERR_BAD_ARG, "bad statistics indexing");
+    const int64_t rows = nseg * nclip;
+    if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
+    if (nsample <= n_fft / 2) return fail(SE_ERR_BAD_ARG, "reflect padding needs nsample > n_fft/2");
+    if ((nseg - 1) * seg_stride >= clip_len) return fail(SE_ERR_BAD_ARG, "last segment starts beyond the clip");
+    int64_t t_lo, t_hi;
+    const int64_t Tg = shared_frames(nseg, seg_stride, nsample, n_fft, hop, t_lo, t_hi);
+    if (Tg <= 0) return fail(SE_ERR_UNSUPPORTED, "shared-frame segment STFT needs seg_stride to be a multiple of hop");
+    const int64_t T = 1 + nsample / hop;
+    const int FRG = (frames8() && ((n_fft == 512 && hop == 128) || (n_fft == 1024 && hop == 256))) ? 8 : 16;    // = G::FR of SE_DISPATCH_GEO
+    const int64_t ng = (T + FRG - 1) / FRG;
+    const int64_t lead = (t_lo + FRG - 1) / FRG;             // leading groups holding boundary frames
+    const int64_t trail0 = (t_hi + 1) / FRG;                 // first trailing group holding a boundary frame
+    if (lead >= trail0) {                                    // short segments: every group is an edge group
+        return se_stft_segments_norm_fwd(x, spec, stats, stats_div, stats_c, nseg, nclip, clip_len, clip_stride, seg_stride, nsample,
+                                         n_fft, hop, win_length, scale, stream);
+    }
+    cudaError_t e;
+    // 1. clip-level transform: frame g covers clip samples [g hop - n/2, g hop + n/2), zero beyond the clip
+    {
+        AnaArgs a{};
+        if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
+        // rows of this launch are clips: seg_rows = nclip makes (seg, clip) = (0, row), which also indexes the statistics
+        a.in = x; a.out = reinterpret_cast<float*>(scratch); a.in_stride = 0; a.clip_stride = clip_stride; a.seg_rows = (int)nclip;
+        a.nsample = (int)clip_len; a.in_len = (int)clip_len; a.nframe = (int)Tg; a.pad = n_fft / 2; a.edge_scale = 1.0f;
+        a.norm = reinterpret_cast<const float4*>(stats); a.norm_div = (int)stats_div; a.norm_c = (int)stats_c;
+        if (stats) SE_DISPATCH_GEO(n_fft, hop, ({ plan_analysis(nclip, Tg, a.gpc, a.nchunks, G::FR);
+                                                 e = launch(k_analysis<G, LOAD_ZEROPAD, false, true>, (unsigned)(nclip * a.nchunks), G::NT, Smem<G>::ANALYSIS, (cudaStream_t)stream, a); }));
+        else SE_DISPATCH_GEO(n_fft, hop, ({ plan_analysis(nclip, Tg, a.gpc, a.nchunks, G::FR);
+                                            e = launch(k_analysis<G, LOAD_ZEROPAD, false, false>, (unsigned)(nclip * a.nchunks), G::NT, Smem<G>::ANALYSIS, (cudaStream_t)stream, a); }));
+        if (e != cudaSuccess) return cuda_fail(e, "se_stft_segments_shared_fwd (clip transform) launch");
+    }
+    // 2. per-segment transform of the groups that hold reflect-boundary frames
+    {
+        AnaArgs a{};
+        if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
+        a.in = x; a.out = spec; a.in_stride = seg_stride; a.clip_stride = clip_stride; a.seg_rows = (int)nclip;
+        a.clip_len = (int)clip_len; a.nsample = (int)nsample; a.in_len = (int)nsample;
+        a.norm = reinterpret_cast<const float4*>(stats); a.norm_div = (int)stats_div; a.norm_c = (int)stats_c;
+        a.nframe = (int)T; a.pad = 0; a.edge_scale = 1.0f;
+        a.gpc = 1; a.edge_lead = (int)lead; a.edge_trail0 = (int)trail0; a.nchunks = (int)(lead + (ng - trail0));
+        if (stats) SE_DISPATCH_GEO(n_fft, hop, (e = launch(k_analysis<G, LOAD_REFLECT, false, true>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, (cudaStream_t)stream, a)));
+        else SE_DISPATCH_GEO(n_fft, hop, (e = launch(k_analysis<G, LOAD_REFLECT, false, false>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS, (cudaStream_t)stream, a)));
+        if (e != cudaSuccess) return cuda_fail(e, "se_stft_segments_shared_fwd (edge groups) launch");
+    }
+    // 3. interior frames: copies out of the clip-level spectrum
+    const int F = n_fft / 2 + 1;
+    const int64_t grows = rows * F;
+    e = launch(k_segment_gather, (unsigned)((grows + kGatherRows - 1) / kGatherRows), 256u, 0, (cudaStream_t)stream,
+               reinterpret_cast<const float2*>(scratch), reinterpret_cast<float2*>(spec), (int)nclip, F, (int)T, (int)Tg,
+               (int)(seg_stride / hop), (int)(lead * FRG), (int)(trail0 * FRG), (int)grows);
+    return e == cudaSuccess ? 0 : cuda_fail(e, "se_stft_segments_shared_fwd (gather) launch");
 }
 
 }  // extern "C"

@@ -45,6 +45,9 @@ struct AnaArgs {            // analysis: waveform-like -> spectrum
     // clip -> statistics row = (clip / norm_div) * norm_c + clip % norm_c.  nullptr: no normalisation.
     const float4* norm;
     int norm_div, norm_c;
+    // evaluate()'s shared-frame path: only the groups that contain reflect-boundary frames are transformed per segment
+    // (chunk c < edge_lead -> group c, else group edge_trail0 + c - edge_lead; one group per chunk); 0 = all groups
+    int edge_lead, edge_trail0;
 };
 
 struct SynArgs {            // synthesis: spectrum -> waveform-like
@@ -130,6 +133,10 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
                 const int j = i - a.pad;
                 v[k] = make_float2((j >= 0 && j < a.nsample) ? __ldg(src + j) : 0.f,
                                    (j + 1 >= 0 && j + 1 < a.nsample) ? __ldg(src + j + 1) : 0.f);
+                if (NORM) {                                  // valid samples are normalised, the zero padding stays zero
+                    if (j >= 0 && j < a.nsample) v[k].x = (v[k].x - nm_mean) * nm_inv;
+                    if (j + 1 >= 0 && j + 1 < a.nsample) v[k].y = (v[k].y - nm_mean) * nm_inv;
+                }
             } else {
                 const int q = i - G::N / 2;
                 v[k] = make_float2((q >= 0 && q < a.in_len && i < a.nsample) ? __ldg(src + q) : 0.f,
@@ -143,7 +150,7 @@ __device__ __forceinline__ void fill_stage(float* __restrict__ stage, const floa
         if (slot >= SLOTS) continue;
         const int rel = 2 * slot;
         float2 w = v[k];
-        if (NORM && LMODE == LOAD_REFLECT && interior) w = make_float2((w.x - nm_mean) * nm_inv, (w.y - nm_mean) * nm_inv);
+        if (NORM && LMODE != LOAD_ENV && interior) w = make_float2((w.x - nm_mean) * nm_inv, (w.y - nm_mean) * nm_inv);
         if (LMODE == LOAD_ENV) {      // gy / envelope (zero where the envelope is empty)
             const int i = p0 + rel;
             w.x *= inv_env_at<G>(a.tb, a.nframe, i);
@@ -532,7 +539,8 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_analysis(const AnaArgs a) {
         nm_inv = st.y;
     }
     for (int g = 0; g < a.gpc; ++g) {
-        const int f_base = (chunk * a.gpc + g) * G::FR;
+        const int group = a.edge_lead ? (chunk < a.edge_lead ? chunk : a.edge_trail0 + chunk - a.edge_lead) : chunk * a.gpc + g;
+        const int f_base = group * G::FR;
         if (f_base >= a.nframe) break;
         fill_stage<G, LMODE, NORM>(stage, src, f_base * G::HOP, a, tid, nvalid, nm_mean, nm_inv);
         __syncthreads();
@@ -683,17 +691,47 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_synthesis_stitch(const SynAr
 
 // per-row mean and unbiased standard deviation (torch.mean / torch.std, src/evaluate.py:19-20), double accumulators:
 // stats[row] = (mean, 1 / (std + 1e-9), std + 1e-9, 0)
-static __global__ void __launch_bounds__(256) k_row_stats(const float* __restrict__ x, float4* __restrict__ stats, int64_t len,
-                                                  int64_t row_stride) {
-    __shared__ double sh[2][8];
+// A row (one channel of a clip, ~0.5 M samples) is summed by a thread-block CLUSTER of 8 CTAs: each CTA streams an eighth
+// of the row (1024 threads x 8 independent 128-bit loads in flight), the partial sums meet in rank 0's shared memory
+// through distributed shared memory and are added in rank order -- deterministic, no global scratch, no atomics.
+#ifdef SE_EMULATE
+constexpr int kStatsCluster = 1;
+#define SE_CLUSTER_DIMS(n)
+#else
+constexpr int kStatsCluster = 8;
+#define SE_CLUSTER_DIMS(n) __cluster_dims__(n, 1, 1)
+#endif
+static __global__ void SE_CLUSTER_DIMS(kStatsCluster) __launch_bounds__(1024) k_row_stats(const float* __restrict__ x,
+                                                                                          float4* __restrict__ stats, int64_t len,
+                                                                                          int64_t row_stride) {
+    __shared__ double sh[2][32];
+    __shared__ double parts[2][kStatsCluster];
     pdl_launch_dependents();
     pdl_wait();
-    const float* row = x + (size_t)blockIdx.x * row_stride;
+    const int rowi = blockIdx.x / kStatsCluster, part = blockIdx.x % kStatsCluster;
+    const float* row = x + (size_t)rowi * row_stride;
     double s1 = 0.0, s2 = 0.0;
-    for (int64_t i = threadIdx.x; i < len; i += 256) {
-        const double v = (double)__ldg(row + i);
-        s1 += v;
-        s2 += v * v;
+    const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+    const int64_t nvec = vec ? len / 4 : 0;
+    const int64_t v0 = nvec * part / kStatsCluster, v1 = nvec * (part + 1) / kStatsCluster;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += 8 * 1024) {
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (i + k * 1024 < v1) ? __ldg(r4 + i + k * 1024) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double a = v[k].x, b = v[k].y, c = v[k].z, d = v[k].w;
+            s1 += (a + b) + (c + d);
+            s2 += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    if (part == kStatsCluster - 1) {                          // scalar tail (or the whole row when it is not 16-byte aligned)
+        for (int64_t i = 4 * nvec + threadIdx.x; i < len; i += 1024) {
+            const double v = (double)__ldg(row + i);
+            s1 += v;
+            s2 += v * v;
+        }
     }
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) {
@@ -704,12 +742,72 @@ static __global__ void __launch_bounds__(256) k_row_stats(const float* __restric
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        for (int w = 0; w < 32; ++w) { a += sh[0][w]; b += sh[1][w]; }
+#ifdef SE_EMULATE
+        parts[0][part] = a;
+        parts[1][part] = b;
+#else
+        // store this CTA's pair into rank 0's shared memory (DSMEM)
+        unsigned local = (unsigned)__cvta_generic_to_shared(&parts[0][0]), remote;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote + 8u * part), "d"(a) : "memory");
+        asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote + 8u * (kStatsCluster + part)), "d"(b) : "memory");
+#endif
+    }
+#ifndef SE_EMULATE
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+    if (part == 0 && threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int c = 0; c < kStatsCluster; ++c) { a += parts[0][c]; b += parts[1][c]; }      // rank order: deterministic
         const double mean = a / (double)len;
         double var = len > 1 ? (b - (double)len * mean * mean) / (double)(len - 1) : 0.0;
         var = var > 0.0 ? var : 0.0;
         const double scale = sqrt(var) + 1e-9;
-        stats[blockIdx.x] = make_float4((float)mean, (float)(1.0 / scale), (float)scale, 0.f);
+        stats[rowi] = make_float4((float)mean, (float)(1.0 / scale), (float)scale, 0.f);
+    }
+}
+
+// evaluate(): interior frames of overlapping segments are frames of ONE clip-level transform (segment s, frame t =
+// clip frame s * stride/hop + t whenever the frame does not touch the segment's reflect padding).  Copies
+// the frame range [t0, t1) of every (segment, clip, bin) row out of the clip-level spectrum glob [nclip][F][Tg].
+constexpr int kGatherRows = 16;                              // rows per block: 418 k one-row blocks were launch-rate bound (3.2 TB/s)
+static __global__ void __launch_bounds__(256) k_segment_gather(const float2* __restrict__ glob, float2* __restrict__ out,
+                                                                int nclip, int nbin, int T, int Tg, int frames_per_seg, int t0, int t1,
+                                                                int nrows) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // 8 warps x 2 rows each; a warp streams one row: 128-bit stores on the (DRAM-bound) output side -- rows of odd T
+    // alternate their 16-byte phase, so a row may start with a 64-bit head -- and 64-bit loads from the L2-resident
+    // clip spectrum
+    for (int r = warp; r < kGatherRows; r += 8) {
+        const int row = blockIdx.x * kGatherRows + r;        // (seg * nclip + clip) * nbin + bin
+        if (row >= nrows) break;
+        const int bin = row % nbin, sc = row / nbin, clip = sc % nclip, seg = sc / nclip;
+        const float2* src = glob + ((size_t)clip * nbin + bin) * Tg + (size_t)seg * frames_per_seg;
+        float2* dst = out + (size_t)row * T;
+        int t = t0;
+        if ((reinterpret_cast<uintptr_t>(dst + t) & 15) != 0) {
+            if (lane == 0 && t < t1) dst[t] = __ldg(src + t);
+            ++t;
+        }
+        const int npair = (t1 - t) / 2;
+        for (int p = lane; p < npair; p += 128) {            // 4 independent pairs per lane in flight
+            float2 a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pp = p + 32 * k;
+                if (pp < npair) { a[k] = __ldg(src + t + 2 * pp); b[k] = __ldg(src + t + 2 * pp + 1); }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pp = p + 32 * k;
+                if (pp < npair) *reinterpret_cast<float4*>(dst + t + 2 * pp) = make_float4(a[k].x, a[k].y, b[k].x, b[k].y);
+            }
+        }
+        if (((t1 - t) & 1) && lane == 0 && t1 > t) dst[t1 - 1] = __ldg(src + t1 - 1);
     }
 }
 

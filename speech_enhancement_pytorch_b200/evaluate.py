@@ -116,10 +116,22 @@ def segment_stft(wave, num_feature, stride, config, stats=None):
     nv.require_cuda_f32(x, stats)
     nf, nt = n_fft // 2 + 1, 1 + num_feature // hop
     out = torch.empty((nseg * nb, nc, nf, nt, 2), dtype=torch.float32, device=x.device)
+    L = nv.lib()
+    sp = 0 if stats is None else stats.data_ptr()
+    # Overlapping segments share all frames that do not touch their reflect padding: transform those ONCE at clip level and
+    # gather (three launches), instead of transforming every frame of every segment (a 30 s clip at stride 512 has 814
+    # segments x 501 frames of which 3 750 are distinct).  Falls back to the per-segment kernel when the stride is no
+    # multiple of the hop or there is nothing to share.
+    scratch_bytes = int(L.se_stft_segments_scratch_bytes(nseg, nb * nc, stride, num_feature, n_fft, hop)) if nseg > 2 else 0
     with nv.on_device(x.device):
-        nv.check(nv.lib().se_stft_segments_norm_fwd(x.data_ptr(), out.data_ptr(), 0 if stats is None else stats.data_ptr(),
-                                                    nb * nc, nb * nc, nseg, nb * nc, length, length, stride, num_feature, n_fft, hop,
-                                                    win, 1.0 / win, nv.stream_ptr(x.device)))
+        if scratch_bytes > 0:
+            scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=x.device)
+            nv.check(L.se_stft_segments_shared_fwd(x.data_ptr(), out.data_ptr(), sp, nb * nc, nb * nc, nseg, nb * nc, length, length,
+                                                   stride, num_feature, n_fft, hop, win, 1.0 / win, scratch.data_ptr(),
+                                                   nv.stream_ptr(x.device)))
+        else:
+            nv.check(L.se_stft_segments_norm_fwd(x.data_ptr(), out.data_ptr(), sp, nb * nc, nb * nc, nseg, nb * nc, length, length,
+                                                 stride, num_feature, n_fft, hop, win, 1.0 / win, nv.stream_ptr(x.device)))
     return out, nseg
 
 

@@ -301,6 +301,20 @@ def stft_segments_norm_fwd(x, stats, nseg, seg_stride, nsample, n, hop, win, sca
     return out
 
 
+def stft_segments_shared_fwd(x, stats, nseg, seg_stride, nsample, n, hop, win, scale):
+    nclip, clip_len = x.shape
+    T = 1 + nsample // hop
+    lib().se_stft_segments_scratch_bytes.restype = ctypes.c_int64
+    nbytes = lib().se_stft_segments_scratch_bytes(i64(nseg), i64(nclip), i64(seg_stride), i64(nsample), ci(n), ci(hop))
+    assert nbytes > 0
+    scratch = np.full(nbytes // 4, np.nan, np.float32)
+    out = np.full((nseg * nclip, n // 2 + 1, T, 2), np.nan, np.float32)
+    check(lib().se_stft_segments_shared_fwd(ptr(x), ptr(out), ptr(stats) if stats is not None else None, i64(nclip), i64(nclip),
+                                            i64(nseg), i64(nclip), i64(clip_len), i64(clip_len), i64(seg_stride), i64(nsample),
+                                            ci(n), ci(hop), ci(win), f32(scale), ptr(scratch), None))
+    return out
+
+
 def istft_stitch_fwd(spec, stats, nseg, nclip, nfeat, stride, out_len, n, hop, win, scale, div=None, chan=None):
     T = spec.shape[-2]
     out = np.full((nclip, out_len), np.nan, np.float32)

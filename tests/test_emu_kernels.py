@@ -525,3 +525,21 @@ def test_emu_two_pass_engine_matches_the_default_engine(n, hop, N, monkeypatch):
     assert rel(c2(out["3"][0]), want) < 1e-6
     for a, b in zip(out["3"], out["1"]):
         assert rel(a, b) < 2e-6
+
+
+@pytest.mark.parametrize("n,hop,nfeat,length,zscore", [(512, 128, 8192, 20000, True), (512, 128, 6144, 15001, False),
+                                                       (1024, 256, 8192, 17000, True)])
+def test_emu_shared_frame_segment_stft_equals_per_segment_transform(n, hop, nfeat, length, zscore):
+    """evaluate()'s segment STFT with the frames shared between overlapping segments transformed once at clip level
+    (clip transform + boundary groups + gather) is BIT-identical to transforming every frame of every segment -- including
+    the zero-filled tail of the last segments and the z-score folded into both fills."""
+    rng = np.random.default_rng(n + length)
+    wav = (0.3 * rng.standard_normal((2, length)) + 0.05).astype(np.float32)
+    stride = n
+    rem = (length - nfeat) % stride
+    nseg = (length + (stride - rem if rem else 0) - nfeat) // stride + 1
+    stats = E.row_stats(wav) if zscore else None
+    a = E.stft_segments_norm_fwd(wav, stats, nseg, stride, nfeat, n, hop, n, 1.0 / n)
+    b = E.stft_segments_shared_fwd(wav, stats, nseg, stride, nfeat, n, hop, n, 1.0 / n)
+    assert not np.isnan(b).any()
+    assert np.array_equal(a, b)
