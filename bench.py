@@ -309,6 +309,16 @@ def run_configs(se, dev, world, group, hbm_peak, fp32_peak):
               us, 240, 16 * (2 * 4 * NL + 8 * F * T), channel_s_per_s=round(480 * world / us * 1e6))
         del sets
         torch.cuda.empty_cache()
+    # ---- cfg5, reference-faithful variant: the reference resamples to 16 kHz and runs evaluate() -- z-score, 4 s
+    # segments at stride win_length = 512 (814 segments of a 30 s clip), STFT, [model], iSTFT, stitch; one stereo clip per GPU
+    conf = types.SimpleNamespace(dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
+                                 model=types.SimpleNamespace(name="unet", segment=4.0, n_fft=512, hop_length=128, win_length=512,
+                                                             center=True, sources=["clean"]))
+    sets = [((0.3 * torch.randn(1, 2, 480000, generator=g) + 0.01).to(dev),) for _ in range(2)]
+    us = timed(lambda s: se.evaluate(s[0], None, dev, conf), sets, reps=10, warm=3)
+    entry("cfg5_evaluate_16k", "se.evaluate(model=None): one 30 s stereo clip at 16 kHz per GPU, 814 segments x 4 s at stride 512 "
+          "(row stats, shared-frame segment STFT, stitching iSTFT)", us, 30, 2 * 4 * 480000 * 2 + 8 * 257 * 501 * 814 * 2,
+          channel_s_per_s=round(60 * world / us * 1e6))
     return out
 
 
@@ -385,6 +395,17 @@ def cpu_configs_parity(se, dev):
         with torch.no_grad():
             got = se.enhance(x.to(dev), m.to(dev), c, "C")
         res.append({"name": f"cfg5_n{n}", "cpu_audio_s_per_s": round(30 / dt), "sample": "1 of 8 clips", "max_rel_err": rel(got, want), "tol": 1e-4})
+    # cfg5 through evaluate(): a 6 s stereo clip (150 segments) against the oracle's restatement of src/evaluate.py:10-98
+    conf = types.SimpleNamespace(dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
+                                 model=types.SimpleNamespace(name="unet", segment=4.0, n_fft=512, hop_length=128, win_length=512,
+                                                             center=True, sources=["clean"]))
+    x = 0.3 * torch.randn(1, 2, 96000, generator=g) + 0.01
+    t0 = time.perf_counter()
+    want = oref.evaluate_ref(x, None, conf)
+    dt = time.perf_counter() - t0
+    got = se.evaluate(x, None, dev, conf)
+    res.append({"name": "cfg5_evaluate_16k", "cpu_audio_s_per_s": round(6 / dt, 1), "sample": "one 6 s stereo clip (63 segments)",
+                "max_rel_err": rel(got, want), "tol": 1e-4})
     return res
 
 
