@@ -528,6 +528,7 @@ def run_ours(args):
     def k_mask(raw): nv.check(L.se_mask_fwd(P(X), P(raw), P(Y), count, 1, 1, st))
     def k_istft(): nv.check(L.se_istft_fwd(P(Y), P(y), rows, T, N, N_FFT, HOP, WIN, float(WIN), st))
     def k_loss_fwd(clean): nv.check(L.se_mrstft_loss_fwd(P(y), P(clean), rows, N, P(sums), P(ws), st))
+    def k_loss_fwd_value(clean): nv.check(L.se_mrstft_loss_fwd_value(P(y), P(clean), rows, N, P(sums), P(loss), P(ws), st))
     def k_loss_val(): nv.check(L.se_mrstft_loss_value(P(sums), rows * world, N, P(loss), st))
     def k_loss_bwd(clean): nv.check(L.se_mrstft_loss_bwd(P(y), P(ws), P(sums), P(one), rows * world, rows, N, P(gy), st))
     def k_istft_bwd(): nv.check(L.se_istft_bwd(P(gy), P(gY), rows, T, N, N_FFT, HOP, WIN, float(WIN), st))
@@ -545,13 +546,15 @@ def run_ours(args):
             k_stft(x); k_tail_fwd(raw)
         else:
             k_stft(x); k_mask(raw); k_istft()
-        k_loss_fwd(clean)
-        if px is not None:
-            px.exchange_value(sums, rows * world, N, loss, st)   # the path's only exchange step, fused with the value
+        if group is None:
+            k_loss_fwd_value(clean)                              # one process: the reduction launch also writes the loss value
         else:
-            if group is not None:
+            k_loss_fwd(clean)
+            if px is not None:
+                px.exchange_value(sums, rows * world, N, loss, st)   # the path's only exchange step, fused with the value
+            else:
                 dist.all_reduce(sums, group=group)
-            k_loss_val()
+                k_loss_val()
         k_loss_bwd(clean)
         if comp == "fused":
             k_enh_bwd(x, raw)
@@ -560,7 +563,8 @@ def run_ours(args):
         else:
             k_istft_bwd(); k_mask_bwd(raw)
 
-    n_launch = {"fused": 2, "tail": 3, "dropin": 5}[comp] + 4 + 1 + 3      # + 3 loss fwd, 1 reduce, value, 3 loss bwd
+    # + 3 loss fwd, 1 reduce (which writes the value when there is one process; else + 1 exchange / value launch), 3 loss bwd
+    n_launch = {"fused": 2, "tail": 3, "dropin": 5}[comp] + 4 + (0 if group is None else 1) + 3
 
     def sync_all():
         torch.cuda.synchronize(dev)

@@ -150,6 +150,10 @@ int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample);
 int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums,
                        void* workspace, void* stream);
 int se_mrstft_loss_value(const double* sums, int64_t global_rows, int64_t nsample, float* loss, void* stream);
+/* Single process (no exchange step): forward + value in the same launches -- the deterministic reduction also writes
+ * the loss, so the step has one launch less than se_mrstft_loss_fwd followed by se_mrstft_loss_value(rows). */
+int se_mrstft_loss_fwd_value(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums, float* loss,
+                             void* workspace, void* stream);
 /* Uneven shards (ranks holding different row counts): keep the count on the device instead of guessing it on the host.
  * sums10 = the 9 sums + [9] the row count; each rank stores its own count there before the exchange (all-reduce or
  * se_mrstft_exchange_rows_value), which leaves the GLOBAL count in [9].  se_mrstft_loss_value_dev reads it from there;

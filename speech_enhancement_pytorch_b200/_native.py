@@ -31,7 +31,7 @@ EXPORTS = (
     "se_conv_stft_fwd", "se_conv_istft_fwd", "se_conv_istft_bwd",
     "se_mask_planar_fwd", "se_mask_planar_bwd", "se_conv_mask_istft_fwd", "se_conv_mask_istft_bwd",
     "se_p2p_create", "se_p2p_open", "se_p2p_close", "se_p2p_destroy", "se_mrstft_exchange_value",
-    "se_mrstft_exchange_rows_value", "se_mrstft_loss_value_dev",
+    "se_mrstft_exchange_rows_value", "se_mrstft_loss_value_dev", "se_mrstft_loss_fwd_value",
     "se_register_window", "se_conv_stft_fwd_w", "se_conv_istft_fwd_w", "se_conv_istft_bwd_w", "se_conv_mask_istft_fwd_w",
     "se_conv_mask_istft_bwd_w", "se_polar_from_planar", "se_planar_from_polar", "se_planar_from_polar_bwd",
 )
@@ -180,6 +180,7 @@ def lib():
             L.se_mask_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _PTR, _I64, _INT, _INT, _PTR]
             L.se_mrstft_loss_fwd.argtypes = [_PTR, _PTR, _I64, _I64, _PTR, _PTR, _PTR]
             L.se_mrstft_loss_value.argtypes = [_PTR, _I64, _I64, _PTR, _PTR]
+            L.se_mrstft_loss_fwd_value.argtypes = [_PTR, _PTR, _I64, _I64, _PTR, _PTR, _PTR, _PTR]
             L.se_mrstft_loss_bwd.argtypes = [_PTR, _PTR, _PTR, _PTR, _I64, _I64, _I64, _PTR, _PTR]
             L.se_spectral_loss_workspace_bytes.restype = _I64
             L.se_spectral_loss_workspace_bytes.argtypes = [_I64, _I64, _INT]

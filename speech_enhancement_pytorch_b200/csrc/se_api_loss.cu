@@ -113,8 +113,22 @@ int64_t se_mrstft_workspace_bytes(int64_t rows, int64_t nsample) {
     return total;
 }
 
+static int loss_fwd_impl(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums, float* loss,
+                         void* workspace, void* stream);
+
 int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums,
                        void* workspace, void* stream) {
+    return loss_fwd_impl(est, ref, rows, nsample, sums, nullptr, workspace, stream);
+}
+// single-process variant: the reduction launch also writes the loss value (no separate se_mrstft_loss_value launch)
+int se_mrstft_loss_fwd_value(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums, float* loss,
+                             void* workspace, void* stream) {
+    if (!loss) return fail(SE_ERR_BAD_ARG, "null pointer");
+    return loss_fwd_impl(est, ref, rows, nsample, sums, loss, workspace, stream);
+}
+
+static int loss_fwd_impl(const float* est, const float* ref, int64_t rows, int64_t nsample, double* sums, float* loss,
+                         void* workspace, void* stream) {
     if (!est || !ref || !sums || !workspace) return fail(SE_ERR_BAD_ARG, "null pointer");
     if (rows <= 0 || nsample < 2048) return fail(SE_ERR_BAD_ARG, "need rows > 0 and nsample >= 2048");
     double* part0 = reinterpret_cast<double*>(workspace);
@@ -145,8 +159,10 @@ int se_mrstft_loss_fwd(const float* est, const float* ref, int64_t rows, int64_t
         if (e != cudaSuccess) return cuda_fail(e, "se_mrstft_loss_fwd launch");
     }
     // plain stream serialisation: the reduction needs ALL three kernels, not just its immediate predecessor
-    cudaError_t e = launch_ex(false, k_reduce_partials, 3u, 256u, 0, (cudaStream_t)stream,
-                              (const double*)part0, nres[0], nres[1], nres[2], sums);
+    double cnt[3];
+    for (int r = 0; r < 3; ++r) cnt[r] = (double)rows * (kRes[r][0] / 2 + 1) * (double)(1 + nsample / kRes[r][1]);
+    cudaError_t e = launch_ex(false, k_reduce_partials, loss ? 1u : 3u, 256u, 0, (cudaStream_t)stream,
+                              (const double*)part0, nres[0], nres[1], nres[2], sums, loss, cnt[0], cnt[1], cnt[2]);
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_mrstft_loss_fwd reduce launch");
 }
 

@@ -1132,25 +1132,39 @@ __global__ void __launch_bounds__(G::NT, G::MINB) k_loss_bwd_saved(const LossArg
     }
 }
 
-// reduce per-CTA partials -> sums[9] in a fixed order (one CTA per resolution, deterministic)
-static __global__ void k_reduce_partials(const double* __restrict__ partials, int n0, int n1, int n2, double* __restrict__ sums) {
+// reduce per-CTA partials -> sums[9] in a fixed order (deterministic).  gridDim.x == 3: one CTA per resolution;
+// gridDim.x == 1: one CTA walks the three resolutions and, when `loss` is given, also evaluates the loss value
+// (c0..c2 = global bins per resolution) -- the single-process step then needs no separate value launch.
+static __global__ void k_reduce_partials(const double* __restrict__ partials, int n0, int n1, int n2, double* __restrict__ sums,
+                                         float* __restrict__ loss, double c0, double c1, double c2) {
     __shared__ double sh[3][256];
+    __shared__ double tot[9];
     pdl_launch_dependents();
     pdl_wait();
-    const int tid = threadIdx.x, r = blockIdx.x;
-    const int n = r == 0 ? n0 : (r == 1 ? n1 : n2);
-    partials += (size_t)3 * (r == 0 ? 0 : (r == 1 ? n0 : n0 + n1));
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int i = tid; i < n; i += 256)
-        for (int j = 0; j < 3; ++j) acc[j] += partials[(size_t)i * 3 + j];
-    for (int j = 0; j < 3; ++j) sh[j][tid] = acc[j];
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
-        if (tid < s)
-            for (int j = 0; j < 3; ++j) sh[j][tid] += sh[j][tid + s];
+    const int tid = threadIdx.x;
+    const int r_lo = gridDim.x == 1 ? 0 : blockIdx.x, r_hi = gridDim.x == 1 ? 3 : blockIdx.x + 1;
+    for (int r = r_lo; r < r_hi; ++r) {
+        const int n = r == 0 ? n0 : (r == 1 ? n1 : n2);
+        const double* part = partials + (size_t)3 * (r == 0 ? 0 : (r == 1 ? n0 : n0 + n1));
+        double acc[3] = {0.0, 0.0, 0.0};
+        for (int i = tid; i < n; i += 256)
+            for (int j = 0; j < 3; ++j) acc[j] += part[(size_t)i * 3 + j];
+        for (int j = 0; j < 3; ++j) sh[j][tid] = acc[j];
+        __syncthreads();
+        for (int s = 128; s > 0; s >>= 1) {
+            if (tid < s)
+                for (int j = 0; j < 3; ++j) sh[j][tid] += sh[j][tid + s];
+            __syncthreads();
+        }
+        if (tid < 3) { sums[3 * r + tid] = sh[tid][0]; tot[3 * r + tid] = sh[tid][0]; }
         __syncthreads();
     }
-    if (tid < 3) sums[3 * r + tid] = sh[tid][0];
+    if (gridDim.x == 1 && loss && tid == 0) {
+        const double cnt[3] = {c0, c1, c2};
+        double total = 0.0;
+        for (int r = 0; r < 3; ++r) total += sqrt(tot[3 * r]) / sqrt(tot[3 * r + 1]) + tot[3 * r + 2] / cnt[r];
+        *loss = (float)(total / 3.0);
+    }
 }
 
 // c0..c2: global bins per resolution; rows_dev != nullptr: they are bins PER ROW and the global row count is read there

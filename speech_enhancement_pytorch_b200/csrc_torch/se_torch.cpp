@@ -199,8 +199,7 @@ struct MrstftFn : torch::autograd::Function<MrstftFn> {
         Tensor sums = at::empty({9}, est.options().dtype(at::kDouble));
         Tensor loss = at::empty({}, est.options());
         void* st = stream_of(est);
-        check(se_mrstft_loss_fwd(cp(est), cp(ref), rows, n, sums.mutable_data_ptr<double>(), ws.mutable_data_ptr(), st));
-        check(se_mrstft_loss_value(sums.const_data_ptr<double>(), rows, n, mp(loss), st));
+        check(se_mrstft_loss_fwd_value(cp(est), cp(ref), rows, n, sums.mutable_data_ptr<double>(), mp(loss), ws.mutable_data_ptr(), st));
         ctx->save_for_backward({est, ws, sums});
         return loss;
     }

@@ -543,3 +543,20 @@ def test_emu_shared_frame_segment_stft_equals_per_segment_transform(n, hop, nfea
     b = E.stft_segments_shared_fwd(wav, stats, nseg, stride, nfeat, n, hop, n, 1.0 / n)
     assert not np.isnan(b).any()
     assert np.array_equal(a, b)
+
+
+def test_emu_mrstft_forward_with_fused_value_matches_two_launch_form():
+    """se_mrstft_loss_fwd_value (one reduction CTA that also writes the loss) against se_mrstft_loss_fwd +
+    se_mrstft_loss_value: same sums bit for bit, same loss."""
+    import ctypes
+    rng = np.random.default_rng(3)
+    ref = rng.standard_normal((3, 5000)).astype(np.float32)
+    est = (ref + 0.1 * rng.standard_normal((3, 5000))).astype(np.float32)
+    sums, loss = E.mrstft_fwd(est, ref)
+    L = E.lib()
+    ws = np.zeros(L.se_mrstft_workspace_bytes(3, 5000) // 8 + 1, np.float64)
+    sums2, loss2 = np.zeros(9, np.float64), np.zeros(1, np.float32)
+    E.check(L.se_mrstft_loss_fwd_value(E.ptr(est), E.ptr(ref), ctypes.c_int64(3), ctypes.c_int64(5000), E.ptr(sums2), E.ptr(loss2),
+                                       E.ptr(ws), None))
+    assert np.array_equal(sums, sums2)
+    assert abs(float(loss2[0]) - float(loss)) <= 1e-7 * abs(float(loss))
