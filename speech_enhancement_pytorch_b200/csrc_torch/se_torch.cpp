@@ -215,6 +215,59 @@ struct MrstftFn : torch::autograd::Function<MrstftFn> {
     }
 };
 
+// ------------------------------------------------------------------ DCCRN in-model transforms (src/model/dccrn.py:669-747)
+Tensor conv_stft_raw(const Tensor& x, int64_t win_len, int64_t win_inc, int64_t fft_len, int64_t window_id) {
+    c10::cuda::CUDAGuard guard(x.device());
+    const int64_t rows = x.size(0), n = x.size(1);
+    const int64_t nt = (n + 2 * (win_len - win_inc) - win_len) / win_inc + 1;
+    Tensor out = at::empty({rows, 2 * (fft_len / 2 + 1), nt}, x.options());
+    check(se_conv_stft_fwd_w(cp(x), mp(out), rows, n, (int)win_len, (int)win_inc, (int)fft_len, (int)window_id, stream_of(x)));
+    return out;
+}
+struct ConvIstftFn : torch::autograd::Function<ConvIstftFn> {
+    static Tensor forward(AutogradContext* ctx, const Tensor& spec, int64_t out_len, int64_t win_len, int64_t win_inc, int64_t fft_len,
+                          int64_t window_id) {
+        c10::cuda::CUDAGuard guard(spec.device());
+        Tensor y = at::empty({spec.size(0), out_len}, spec.options());
+        check(se_conv_istft_fwd_w(cp(spec), mp(y), spec.size(0), spec.size(2), out_len, (int)win_len, (int)win_inc, (int)fft_len,
+                                  (int)window_id, stream_of(spec)));
+        ctx->saved_data["cfg"] = std::vector<int64_t>{spec.size(2), win_len, win_inc, fft_len, window_id};
+        return y;
+    }
+    static variable_list backward(AutogradContext* ctx, variable_list g) {
+        const auto c = ctx->saved_data["cfg"].toIntVector();
+        const Tensor gy = g[0].contiguous();
+        c10::cuda::CUDAGuard guard(gy.device());
+        Tensor gs = at::empty({gy.size(0), 2 * (c[3] / 2 + 1), c[0]}, gy.options());
+        check(se_conv_istft_bwd_w(cp(gy), mp(gs), gy.size(0), c[0], gy.size(1), (int)c[1], (int)c[2], (int)c[3], (int)c[4], stream_of(gy)));
+        return {gs, Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+    }
+};
+// DCCRN's mask tail (dccrn.py:203-223) + ConviSTFT (:224) in one launch each way; gradient to the two mask planes
+struct ConvMaskIstftFn : torch::autograd::Function<ConvMaskIstftFn> {
+    static Tensor forward(AutogradContext* ctx, const Tensor& spec, const Tensor& mre, const Tensor& mim, int64_t out_len,
+                          int64_t win_len, int64_t win_inc, int64_t fft_len, int64_t mode, int64_t window_id) {
+        c10::cuda::CUDAGuard guard(spec.device());
+        Tensor y = at::empty({spec.size(0), out_len}, spec.options());
+        check(se_conv_mask_istft_fwd_w(cp(spec), cp(mre), cp(mim), mp(y), spec.size(0), spec.size(2), out_len, (int)win_len, (int)win_inc,
+                                       (int)fft_len, (int)mode, (int)window_id, stream_of(spec)));
+        ctx->save_for_backward({spec, mre, mim});
+        ctx->saved_data["cfg"] = std::vector<int64_t>{out_len, win_len, win_inc, fft_len, mode, window_id};
+        return y;
+    }
+    static variable_list backward(AutogradContext* ctx, variable_list g) {
+        const auto saved = ctx->get_saved_variables();
+        const Tensor &spec = saved[0], &mre = saved[1], &mim = saved[2];
+        const auto c = ctx->saved_data["cfg"].toIntVector();
+        c10::cuda::CUDAGuard guard(spec.device());
+        const Tensor gy = g[0].contiguous();
+        Tensor gre = at::empty_like(mre), gim = at::empty_like(mim);
+        check(se_conv_mask_istft_bwd_w(cp(gy), cp(spec), cp(mre), cp(mim), mp(gre), mp(gim), spec.size(0), spec.size(2), c[0], (int)c[1],
+                                       (int)c[2], (int)c[3], (int)c[4], (int)c[5], stream_of(spec)));
+        return {Tensor(), gre, gim, Tensor(), Tensor(), Tensor(), Tensor(), Tensor(), Tensor()};
+    }
+};
+
 bool needs_grad(std::initializer_list<const Tensor*> ts) {
     if (!at::GradMode::is_enabled()) return false;
     for (const Tensor* t : ts)
@@ -256,9 +309,29 @@ Tensor op_mrstft(const Tensor& est, const Tensor& ref) {
     return MrstftFn::apply(prep(est, "enhanced"), prep(ref, "sources"));
 }
 
+Tensor op_conv_stft(const Tensor& x, int64_t win_len, int64_t win_inc, int64_t fft_len, int64_t window_id) {
+    TORCH_CHECK_VALUE(x.dim() == 2, "se_b200::conv_stft expects [rows, N]");
+    TORCH_CHECK_NOT_IMPLEMENTED(!(at::GradMode::is_enabled() && x.requires_grad()),
+                                "ConvSTFT: gradient wrt the input waveform is not built (the mixture is data)");
+    return conv_stft_raw(prep(x, "input"), win_len, win_inc, fft_len, window_id);
+}
+Tensor op_conv_istft(const Tensor& spec, int64_t out_len, int64_t win_len, int64_t win_inc, int64_t fft_len, int64_t window_id) {
+    TORCH_CHECK_VALUE(spec.dim() == 3, "se_b200::conv_istft expects [rows, 2F, T]");
+    return ConvIstftFn::apply(prep(spec, "spectrum"), out_len, win_len, win_inc, fft_len, window_id);
+}
+Tensor op_conv_mask_istft(const Tensor& spec, const Tensor& mre, const Tensor& mim, int64_t out_len, int64_t win_len, int64_t win_inc,
+                          int64_t fft_len, int64_t mode, int64_t window_id) {
+    TORCH_CHECK_VALUE(spec.dim() == 3 && mre.dim() == 3 && mim.dim() == 3, "se_b200::conv_mask_istft expects [rows, 2F, T] and two [rows, F, T] masks");
+    return ConvMaskIstftFn::apply(prep(spec, "spectrum"), prep(mre, "mask"), prep(mim, "mask"), out_len, win_len, win_inc, fft_len, mode,
+                                  window_id);
+}
+
 }  // namespace
 
 TORCH_LIBRARY(se_b200, m) {
+    m.def("conv_stft(Tensor x, int win_len, int win_inc, int fft_len, int window_id) -> Tensor");
+    m.def("conv_istft(Tensor spec, int out_len, int win_len, int win_inc, int fft_len, int window_id) -> Tensor");
+    m.def("conv_mask_istft(Tensor spec, Tensor mask_re, Tensor mask_im, int out_len, int win_len, int win_inc, int fft_len, int mode, int window_id) -> Tensor");
     m.def("stft(Tensor x, int n_fft, int hop, int win_length, float scale) -> Tensor");
     m.def("istft(Tensor spec, int length, int n_fft, int hop, int win_length, float scale) -> Tensor");
     m.def("mask(Tensor spec, Tensor mask, int mode, bool pre_tanh) -> Tensor");
@@ -275,4 +348,7 @@ TORCH_LIBRARY_IMPL(se_b200, CompositeImplicitAutograd, m) {
     m.impl("mask_istft", op_mask_istft);
     m.impl("enhance", op_enhance);
     m.impl("mrstft_loss", op_mrstft);
+    m.impl("conv_stft", op_conv_stft);
+    m.impl("conv_istft", op_conv_istft);
+    m.impl("conv_mask_istft", op_conv_mask_istft);
 }

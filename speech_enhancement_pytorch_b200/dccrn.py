@@ -64,10 +64,8 @@ class ConvSTFT(torch.nn.Module):
             if inputs.shape[1] != 1:
                 raise RuntimeError("ConvSTFT expects [B,N] or [B,1,N]")
             inputs = inputs[:, 0]
-        if torch.is_grad_enabled() and inputs.requires_grad:
-            # the reference's conv1d is differentiable wrt the waveform; the analysis kernel has no adjoint wired here
-            raise NotImplementedError("ConvSTFT: gradient wrt the input waveform is not built (the mixture is data)")
-        out = ops.conv_stft_rows(ops._as_f32(inputs).contiguous(), self.win_len, self.stride, self.fft_len, self._wid())
+        # (the reference's conv1d is differentiable wrt the waveform; the op raises NotImplementedError for that)
+        out = ops.conv_stft_rows(inputs, self.win_len, self.stride, self.fft_len, self._wid())
         if self.feature_type == "complex":
             return out
         return ops.polar_from_planar(out)                       # (mags, phase), dccrn.py:696-701, one launch

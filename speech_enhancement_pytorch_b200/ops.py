@@ -406,14 +406,7 @@ def register_window(values):
 
 
 def conv_stft_rows(x, win_len, win_inc, fft_len, window_id=0):
-    nv.require_cuda_f32(x)
-    rows, n = x.shape
-    nt = (n + 2 * (win_len - win_inc) - win_len) // win_inc + 1
-    out = torch.empty((rows, 2 * (fft_len // 2 + 1), nt), dtype=torch.float32, device=x.device)
-    with nv.on_device(x.device):
-        nv.check(nv.lib().se_conv_stft_fwd_w(x.data_ptr(), out.data_ptr(), rows, n, win_len, win_inc, fft_len, window_id,
-                                             nv.stream_ptr(x.device)))
-    return out
+    return nv.torch_ops().conv_stft(x, win_len, win_inc, fft_len, window_id)
 
 
 def polar_from_planar(spec):
@@ -460,64 +453,10 @@ def planar_from_polar(mags, phase):
     return _PlanarFromPolar.apply(_as_f32(mags).contiguous(), _as_f32(phase).contiguous())
 
 
-class _ConvISTFT(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, spec, out_len, win_len, win_inc, fft_len, window_id):
-        nv.require_cuda_f32(spec)
-        rows, _, nt = spec.shape
-        y = torch.empty((rows, out_len), dtype=torch.float32, device=spec.device)
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_conv_istft_fwd_w(spec.data_ptr(), y.data_ptr(), rows, nt, out_len, win_len, win_inc,
-                                                  fft_len, window_id, nv.stream_ptr(spec.device)))
-        ctx.cfg = (nt, win_len, win_inc, fft_len, window_id)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        nt, win_len, win_inc, fft_len, window_id = ctx.cfg
-        gy = gy.contiguous()
-        rows, out_len = gy.shape
-        g = torch.empty((rows, 2 * (fft_len // 2 + 1), nt), dtype=torch.float32, device=gy.device)
-        with nv.on_device(gy.device):
-            nv.check(nv.lib().se_conv_istft_bwd_w(gy.data_ptr(), g.data_ptr(), rows, nt, out_len, win_len, win_inc,
-                                                  fft_len, window_id, nv.stream_ptr(gy.device)))
-        return g, None, None, None, None, None
-
-
-class _ConvMaskISTFT(torch.autograd.Function):
-    """ConviSTFT(apply_mask_dccrn(specs, mask_re, mask_im)) in one launch each way; gradient to the two mask planes."""
-
-    @staticmethod
-    def forward(ctx, spec, mre, mim, out_len, win_len, win_inc, fft_len, mode, window_id):
-        nv.require_cuda_f32(spec, mre, mim)
-        rows, _, nt = spec.shape
-        y = torch.empty((rows, out_len), dtype=torch.float32, device=spec.device)
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_conv_mask_istft_fwd_w(spec.data_ptr(), mre.data_ptr(), mim.data_ptr(), y.data_ptr(), rows, nt,
-                                                       out_len, win_len, win_inc, fft_len, mode, window_id,
-                                                       nv.stream_ptr(spec.device)))
-        ctx.save_for_backward(spec, mre, mim)
-        ctx.cfg = (out_len, win_len, win_inc, fft_len, mode, window_id)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        spec, mre, mim = ctx.saved_tensors
-        out_len, win_len, win_inc, fft_len, mode, window_id = ctx.cfg
-        rows, _, nt = spec.shape
-        gy = gy.contiguous()
-        gre, gim = torch.empty_like(mre), torch.empty_like(mim)
-        with nv.on_device(spec.device):
-            nv.check(nv.lib().se_conv_mask_istft_bwd_w(gy.data_ptr(), spec.data_ptr(), mre.data_ptr(), mim.data_ptr(),
-                                                       gre.data_ptr(), gim.data_ptr(), rows, nt, out_len, win_len, win_inc,
-                                                       fft_len, mode, window_id, nv.stream_ptr(spec.device)))
-        return None, gre, gim, None, None, None, None, None, None
-
-
 def conv_mask_istft_rows(spec, mask_real, mask_imag, out_len, win_len, win_inc, fft_len, mode, window_id=0):
-    return _ConvMaskISTFT.apply(_as_f32(spec).contiguous(), _as_f32(mask_real).contiguous(), _as_f32(mask_imag).contiguous(),
-                                int(out_len), win_len, win_inc, fft_len, nv.MASK_MODES[mode], window_id)
+    return nv.torch_ops().conv_mask_istft(spec, mask_real, mask_imag, int(out_len), win_len, win_inc, fft_len, nv.MASK_MODES[mode],
+                                          window_id)
 
 
 def conv_istft_rows(spec, out_len, win_len, win_inc, fft_len, window_id=0):
-    return _ConvISTFT.apply(_as_f32(spec).contiguous(), int(out_len), win_len, win_inc, fft_len, window_id)
+    return nv.torch_ops().conv_istft(spec, int(out_len), win_len, win_inc, fft_len, window_id)
