@@ -45,6 +45,16 @@ typedef enum se_mask_mode {   /* SURVEY.md 8a row a5 */
 int se_version(void);
 const char* se_last_error(void);
 
+/* ---- geometries.  The tuned engine is compiled for n_fft 512 / 1024 / 2048 at hop n_fft/4 or n_fft/2 (and DCCRN's
+ * ConvSTFT / ConviSTFT 400/100/512); every other geometry the reference's signatures accept -- any power-of-two n_fft in
+ * 8 .. 8192, any 1 <= hop <= n_fft, any win_length <= n_fft; any win_len / win_inc / power-of-two fft_len for the DCCRN
+ * transforms -- runs on the general path (csrc/se_generic.cuh) behind the SAME entry points: se_stft_fwd / se_stft_bwd /
+ * se_istft_fwd / se_istft_bwd and se_conv_stft_fwd_w / se_conv_istft_fwd_w / se_conv_istft_bwd_w.  The fused entry
+ * points (enhance, mask_istft, conv_mask_istft, the losses, the segment transforms) exist for tuned geometries only;
+ * the host side composes them from the plain transforms otherwise.  These two report which case applies (1 = tuned). */
+int se_geometry_tuned(int n_fft, int hop);
+int se_conv_geometry_tuned(int win_len, int win_inc, int fft_len);
+
 /* ---- replaces torch.stft inside stft_custom(tensor, config), src/evaluate.py:101-128 --------
  * x [rows,N] -> spec [rows,F,T,2] = scale * rfft(hann(win_length) * reflect-padded frames).
  * The reference uses scale = 1/win_length (src/evaluate.py:120). */

@@ -13,8 +13,8 @@ extern "C" int se_conv_stft_fwd(const float* x, float* spec, int64_t rows, int64
 extern "C" int se_conv_stft_fwd_w(const float* x, float* spec, int64_t rows, int64_t nsample, int win_len, int win_inc, int fft_len,
                      int window_id, void* stream) {
     if (!x || !spec || rows <= 0 || nsample <= 0) return fail(SE_ERR_BAD_ARG, "null pointer or empty tensor");
-    if (fft_len != 512 || win_len > fft_len || win_len < win_inc)
-        return fail(SE_ERR_UNSUPPORTED, "ConvSTFT: fft_len must be 512 and win_inc <= win_len <= fft_len");
+    if (fft_len != 512 || (win_inc != 100 && win_inc != 128) || win_len > fft_len || win_len < win_inc)
+        return gen_conv_stft_fwd(x, spec, rows, nsample, win_len, win_inc, fft_len, window_id, (cudaStream_t)stream);
     const int pad = win_len - win_inc;
     const int64_t T = (nsample + 2 * pad - win_len) / win_inc + 1;
     if (T <= 0) return fail(SE_ERR_BAD_ARG, "ConvSTFT: input shorter than one frame");
@@ -33,7 +33,7 @@ extern "C" int se_conv_stft_fwd_w(const float* x, float* spec, int64_t rows, int
         e = launch(k_analysis<G, LOAD_ZEROPAD, true>, (unsigned)(rows * a.nchunks), G::NT, Smem<G>::ANALYSIS,
                    (cudaStream_t)stream, a);
     } else {
-        return fail(SE_ERR_UNSUPPORTED, "ConvSTFT: win_inc must be 100 or 128");
+        return fail(SE_ERR_UNSUPPORTED, "ConvSTFT: unreachable geometry");
     }
     return e == cudaSuccess ? 0 : cuda_fail(e, "se_conv_stft_fwd launch");
 }
@@ -58,6 +58,8 @@ extern "C" int se_conv_istft_fwd(const float* spec, float* y, int64_t rows, int6
 extern "C" int se_conv_istft_fwd_w(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t out_len, int win_len,
                       int win_inc, int fft_len, int window_id, void* stream) {
     if (!spec || !y) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (!se_conv_geometry_tuned(win_len, win_inc, fft_len))
+        return gen_conv_istft_fwd(spec, y, rows, nframe, out_len, win_len, win_inc, fft_len, window_id, (cudaStream_t)stream);
     ConvArgs a{};
     if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len, window_id)) return rc;
     a.in = spec; a.out = y;
@@ -74,6 +76,8 @@ extern "C" int se_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, in
 extern "C" int se_conv_istft_bwd_w(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t out_len, int win_len,
                       int win_inc, int fft_len, int window_id, void* stream) {
     if (!gy || !gspec) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (!se_conv_geometry_tuned(win_len, win_inc, fft_len))
+        return gen_conv_istft_bwd(gy, gspec, rows, nframe, out_len, win_len, win_inc, fft_len, window_id, (cudaStream_t)stream);
     ConvArgs a{};
     if (int rc = conv_args(a, rows, nframe, out_len, win_len, win_inc, fft_len, window_id)) return rc;
     a.in = gy; a.out = gspec;

@@ -110,6 +110,7 @@ extern "C" {
 int se_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
                 float scale, void* stream) {
     if (!x || !spec) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (!geometry_tuned(n_fft, hop)) return gen_stft_fwd(x, spec, rows, nsample, n_fft, hop, win_length, scale, (cudaStream_t)stream);
     if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
     if (nsample <= n_fft / 2) return fail(SE_ERR_BAD_ARG, "reflect padding needs nsample > n_fft/2");
     AnaArgs a{};
@@ -185,8 +186,10 @@ int se_stft_segments_norm_fwd(const float* x, float* spec, const float* stats, i
 int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
                 float scale, int accumulate, void* stream) {
     if (!gspec || !gx) return fail(SE_ERR_BAD_ARG, "null pointer");
+    // the tuned adjoint needs nsample >= n_fft (its reflect fold stays inside the edge chunks); shorter rows take the general path
+    if (!geometry_tuned(n_fft, hop) || nsample < n_fft)
+        return gen_stft_bwd(gspec, gx, rows, nsample, n_fft, hop, win_length, scale, accumulate, (cudaStream_t)stream);
     if (int rc = check_common(rows, nsample, n_fft, hop, win_length)) return rc;
-    if (nsample < n_fft) return fail(SE_ERR_UNSUPPORTED, "adjoint needs nsample >= n_fft");
     SynArgs a{};
     if (int rc = get_tables(n_fft, hop, win_length, false, 0.5f * scale, a.tb)) return rc;
     a.in = gspec; a.out = gx; a.nsample = (int)nsample; a.out_len = (int)nsample;
@@ -200,6 +203,7 @@ int se_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, in
 int se_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t length, int n_fft, int hop,
                  int win_length, float scale, void* stream) {
     if (!spec || !y) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (!geometry_tuned(n_fft, hop)) return gen_istft_fwd(spec, y, rows, nframe, length, n_fft, hop, win_length, scale, (cudaStream_t)stream);
     if (nframe <= 0 || length <= 0) return fail(SE_ERR_BAD_ARG, "nframe and length must be positive");
     if (int rc = check_common(rows, length, n_fft, hop, win_length)) return rc;
     if (!envelope_ok(n_fft, hop, win_length, false, nframe, n_fft / 2, n_fft / 2 + length, 1e-11))
@@ -217,6 +221,7 @@ int se_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int6
 int se_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t length, int n_fft, int hop,
                  int win_length, float scale, void* stream) {
     if (!gy || !gspec) return fail(SE_ERR_BAD_ARG, "null pointer");
+    if (!geometry_tuned(n_fft, hop)) return gen_istft_bwd(gy, gspec, rows, nframe, length, n_fft, hop, win_length, scale, (cudaStream_t)stream);
     if (nframe <= 0 || length <= 0) return fail(SE_ERR_BAD_ARG, "nframe and length must be positive");
     if (int rc = check_common(rows, length, n_fft, hop, win_length)) return rc;
     AnaArgs a{};

@@ -37,7 +37,7 @@ static std::mutex g_win_mu;
 static std::vector<std::vector<double>> g_windows;
 
 int register_window(const double* values, int win_len) {
-    if (!values || win_len < 2 || win_len > 2048) return fail(SE_ERR_BAD_ARG, "window: need 2 <= win_len <= 2048 values");
+    if (!values || win_len < 2 || win_len > 8192) return fail(SE_ERR_BAD_ARG, "window: need 2 <= win_len <= 8192 values");
     std::lock_guard<std::mutex> lock(g_win_mu);
     for (size_t i = 0; i < g_windows.size(); ++i)
         if ((int)g_windows[i].size() == win_len && std::memcmp(g_windows[i].data(), values, sizeof(double) * win_len) == 0)
@@ -59,6 +59,10 @@ static bool host_window(int n, int win_len, bool front, std::vector<double>& w, 
     const double two_pi = 6.283185307179586476925286766559;
     for (int j = 0; j < win_len; ++j) w[left + j] = 0.5 - 0.5 * std::cos(two_pi * j / win_len);
     return true;
+}
+
+bool host_window_values(int n, int win_len, bool front, std::vector<double>& w, int window_id) {
+    return host_window(n, win_len, front, w, window_id);
 }
 
 // `scale` multiplies the window; front=true puts a short window at the start of the frame (DCCRN)

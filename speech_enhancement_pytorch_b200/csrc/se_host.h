@@ -5,6 +5,7 @@
 #include "se_kernels3.cuh"
 
 #include <string>
+#include <vector>
 
 namespace se {
 
@@ -26,6 +27,24 @@ int plan_synthesis(int64_t rows, int nb, int ola, int ctas_per_sm, int frames_pe
 int engine_version();
 int frames8();
 int check_common(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length);
+bool host_window_values(int n, int win_len, bool front, std::vector<double>& w, int window_id);
+
+// ---- general-geometry path (se_api_generic.cu): any power-of-two n_fft, any hop / win_length; the tuned engine only
+// exists for n_fft 512 / 1024 / 2048 at hop n/4, n/2 (and DCCRN's 400/100/512)
+bool geometry_tuned(int n_fft, int hop);
+int gen_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length, float scale, cudaStream_t st);
+int gen_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length, float scale,
+                 int accumulate, cudaStream_t st);
+int gen_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t length, int n_fft, int hop, int win_length,
+                  float scale, cudaStream_t st);
+int gen_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t length, int n_fft, int hop, int win_length,
+                  float scale, cudaStream_t st);
+int gen_conv_stft_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int win_len, int win_inc, int fft_len,
+                      int window_id, cudaStream_t st);
+int gen_conv_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t out_len, int win_len, int win_inc,
+                       int fft_len, int window_id, cudaStream_t st);
+int gen_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, int64_t out_len, int win_len, int win_inc,
+                       int fft_len, int window_id, cudaStream_t st);
 
 // MODE (0..3) x TANH -> compile-time template arguments
 #define SE_DISPATCH_MASK(mode, pre_tanh, CALL)                                         \

@@ -19,6 +19,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <mutex>
+#include <map>
 #include <set>
 #include <utility>
 
@@ -127,15 +128,16 @@ inline cudaError_t launch_ex(bool pdl, void (*kern)(Params...), unsigned grid, u
         // opt in to large dynamic shared memory once per (device, kernel); keeps the steady-state
         // launch path free of driver calls (and CUDA-graph capturable)
         static std::mutex mu;
-        static std::set<std::pair<int, const void*>> done;
+        static std::map<std::pair<int, const void*>, size_t> done;      // largest size opted in so far
         int dev = 0;
         cudaGetDevice(&dev);
         std::lock_guard<std::mutex> lock(mu);
         const auto key = std::make_pair(dev, reinterpret_cast<const void*>(kern));
-        if (!done.count(key)) {
+        auto it = done.find(key);
+        if (it == done.end() || it->second < smem) {          // kernels with a run-time working set (se_generic.cuh) grow it
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            done.insert(key);
+            done[key] = smem;
         }
     }
     cudaLaunchConfig_t cfg{};

@@ -43,11 +43,14 @@ void* stream_of(const Tensor& t) { return c10::cuda::getCurrentCUDAStream(t.get_
 const float* cp(const Tensor& t) { return t.const_data_ptr<float>(); }
 float* mp(Tensor& t) { return t.mutable_data_ptr<float>(); }
 
-void check_cfg(int64_t n_fft, int64_t hop, int64_t win) {
-    TORCH_CHECK_NOT_IMPLEMENTED(n_fft == 512 || n_fft == 1024 || n_fft == 2048, "n_fft=", n_fft,
-                                ": only 512/1024/2048 are built (no fallback path)");
-    TORCH_CHECK_NOT_IMPLEMENTED(hop * 4 == n_fft || hop * 2 == n_fft, "hop_length=", hop, ": only n_fft/4 and n_fft/2 are built");
+// fused = nullptr: any geometry the general path takes; otherwise the name of a fused op built for the tuned geometries only
+void check_cfg(int64_t n_fft, int64_t hop, int64_t win, const char* fused = nullptr) {
+    TORCH_CHECK_NOT_IMPLEMENTED(n_fft >= 8 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0, "n_fft=", n_fft,
+                                ": powers of two in 8..8192 are built (no CPU / cuFFT fallback path)");
+    TORCH_CHECK_NOT_IMPLEMENTED(hop >= 1 && hop <= n_fft, "hop_length=", hop, " must be in [1, n_fft]");
     TORCH_CHECK_NOT_IMPLEMENTED(win >= 2 && win <= n_fft, "win_length=", win, " must be in [2, n_fft]");
+    TORCH_CHECK_NOT_IMPLEMENTED(!fused || se_geometry_tuned((int)n_fft, (int)hop), fused,
+                                ": built for n_fft 512/1024/2048 at hop n_fft/4 or n_fft/2, got ", n_fft, "/", hop);
 }
 
 // ------------------------------------------------------------------ raw calls
@@ -297,11 +300,11 @@ Tensor op_mask(const Tensor& spec, const Tensor& mask, int64_t mode, bool pre_ta
 }
 Tensor op_mask_istft(const Tensor& spec, const Tensor& mask, int64_t length, int64_t n_fft, int64_t hop, int64_t win, double scale,
                      int64_t mode, bool pre_tanh) {
-    check_cfg(n_fft, hop, win);
+    check_cfg(n_fft, hop, win, "mask_istft");
     return MaskIstftFn::apply(prep(spec, "spectrum"), prep(mask, "mask"), length, n_fft, hop, win, scale, mode, pre_tanh);
 }
 Tensor op_enhance(const Tensor& x, const Tensor& mask, int64_t n_fft, int64_t hop, int64_t win, int64_t mode, bool pre_tanh) {
-    check_cfg(n_fft, hop, win);
+    check_cfg(n_fft, hop, win, "enhance");
     return EnhanceFn::apply(prep(x, "input"), prep(mask, "mask"), n_fft, hop, win, mode, pre_tanh);
 }
 Tensor op_mrstft(const Tensor& est, const Tensor& ref) {

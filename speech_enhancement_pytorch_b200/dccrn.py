@@ -112,7 +112,8 @@ class ConviSTFT(torch.nn.Module):
         from .masking import apply_mask_dccrn
         if mode not in ("E", "C", "R"):
             raise ValueError(f"unknown DCCRN masking mode {mode!r}")
-        if specs.requires_grad:
+        if specs.requires_grad or not ops.conv_is_tuned(self.win_len, self.stride, self.fft_len):
+            # (general geometries: mask kernel, then the transform)
             return self(apply_mask_dccrn(specs, mask_real, mask_imag, mode))
         want = (specs.shape[0], specs.shape[1] // 2, specs.shape[2])
         if specs.dim() != 3 or tuple(mask_real.shape) != want or tuple(mask_imag.shape) != want:

@@ -47,6 +47,13 @@ def stft_custom_with_feature(tensor, config, kind):
     nv.require_cuda_f32(x)
     rows = x.shape[0]
     nf, nt = n_fft // 2 + 1, 1 + nsample // hop
+    if not ops.is_tuned(n_fft, hop):                            # general geometry: transform, then the feature kernel
+        spec = ops.stft(x, n_fft, hop, win, 1.0 / win)
+        feat = torch.empty((rows, nf, nt), dtype=torch.float32, device=x.device)
+        with nv.on_device(x.device):
+            nv.check(nv.lib().se_magnitude_feature(spec.data_ptr(), feat.data_ptr(), rows * nf * nt, nv.FEATURE_KINDS[kind],
+                                                   nv.stream_ptr(x.device)))
+        return spec.reshape(*lead, nf, nt, 2), feat.reshape(*lead, nf, nt)
     spec = torch.empty((rows, nf, nt, 2), dtype=torch.float32, device=x.device)
     feat = torch.empty((rows, nf, nt), dtype=torch.float32, device=x.device)
     with nv.on_device(x.device):
@@ -101,7 +108,7 @@ def segment_stft(wave, num_feature, stride, config, stats=None):
     import torch
     from . import _native as nv
     n_fft, hop, win = _cfg(config)
-    ops._check_cfg(n_fft, hop, win)
+    ops._check_cfg(n_fft, hop, win, tuned_only="evaluate() / segment_stft")
     if wave.dim() != 3:
         raise ValueError("segment_stft expects [B,C,L]")
     if torch.is_grad_enabled() and wave.requires_grad:
@@ -143,7 +150,7 @@ def istft_stitch(spec, nseg, num_feature, stride, out_len, config, stats=None, s
     import torch
     from . import _native as nv
     n_fft, hop, win = _cfg(config)
-    ops._check_cfg(n_fft, hop, win)
+    ops._check_cfg(n_fft, hop, win, tuned_only="evaluate() / istft_stitch")
     s = ops._as_f32(spec).contiguous()
     nv.require_cuda_f32(s, stats)
     nf, nt = s.shape[-3], s.shape[-2]

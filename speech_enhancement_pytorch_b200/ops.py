@@ -16,13 +16,23 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def _check_cfg(n_fft, hop, win_length):
-    if n_fft not in (512, 1024, 2048):
-        raise NotImplementedError(f"n_fft={n_fft}: only 512/1024/2048 are built (no fallback path)")
-    if hop * 4 != n_fft and hop * 2 != n_fft:
-        raise NotImplementedError(f"hop_length={hop}: only n_fft/4 and n_fft/2 are built")
+def is_tuned(n_fft, hop):
+    """True where the tuned engine is compiled (n_fft 512/1024/2048 at hop n/4 or n/2); every other power-of-two
+    geometry runs on the general path behind the same entry points (csrc/se_generic.cuh)."""
+    return n_fft in (512, 1024, 2048) and (hop * 4 == n_fft or hop * 2 == n_fft)
+
+
+def _check_cfg(n_fft, hop, win_length, tuned_only=None):
+    """tuned_only: name of a fused op that only exists for the tuned geometries."""
+    if n_fft < 8 or n_fft > 8192 or (n_fft & (n_fft - 1)):
+        raise NotImplementedError(f"n_fft={n_fft}: powers of two in 8..8192 are built (no CPU / cuFFT fallback path)")
+    if not (1 <= hop <= n_fft):
+        raise NotImplementedError(f"hop_length={hop} must be in [1, n_fft]")
     if not (2 <= win_length <= n_fft):
         raise NotImplementedError(f"win_length={win_length} must be in [2, n_fft]")
+    if tuned_only and not is_tuned(n_fft, hop):
+        raise NotImplementedError(f"{tuned_only}: built for n_fft 512/1024/2048 at hop n_fft/4 or n_fft/2 (got {n_fft}/{hop}); "
+                                  "the plain transforms (stft_custom / istft_custom / apply_mask) take any geometry")
 
 
 # ------------------------------------------------------------------ raw calls
@@ -248,7 +258,7 @@ class _SpectralLoss(torch.autograd.Function):
 
 
 def spectral_loss_rows(enh_rows, target_rows, n_fft, hop, win_length, kind, group=None):
-    _check_cfg(n_fft, hop, win_length)
+    _check_cfg(n_fft, hop, win_length, tuned_only="spectral loss")
     if target_rows.requires_grad:
         raise NotImplementedError("spectral loss: gradient flows to the enhanced spectrum only")
     return _SpectralLoss.apply(_as_f32(enh_rows).contiguous(), _as_f32(target_rows).contiguous(), n_fft, hop, win_length,
@@ -334,6 +344,10 @@ def enhance_rows(x_rows, mask_rows, n_fft, hop, win_length, mode, pre_tanh=False
     _check_cfg(n_fft, hop, win_length)
     if mode not in nv.MASK_MODES:
         raise ValueError(f"unknown masking mode {mode!r}")
+    if not is_tuned(n_fft, hop):
+        # general geometry: the three stages run as three launches (each one differentiable)
+        spec = stft(x_rows, n_fft, hop, win_length, 1.0 / win_length)
+        return istft(mask_apply(spec, mask_rows, mode, pre_tanh), x_rows.shape[-1], n_fft, hop, win_length, float(win_length))
     return nv.torch_ops().enhance(x_rows, mask_rows, n_fft, hop, win_length, nv.MASK_MODES[mode], bool(pre_tanh))
 
 
@@ -342,8 +356,8 @@ def mask_istft_rows(spec, mask, length, n_fft, hop, win_length, scale, mode, pre
     _check_cfg(n_fft, hop, win_length)
     if mode not in nv.MASK_MODES:
         raise ValueError(f"unknown masking mode {mode!r}")
-    if spec.requires_grad:
-        # the spectrum itself is being trained through: keep the two differentiable stages separate
+    if spec.requires_grad or not is_tuned(n_fft, hop):
+        # the spectrum itself is being trained through (or a general geometry): keep the two differentiable stages separate
         return istft(mask_apply(spec, mask, mode, pre_tanh), length, n_fft, hop, win_length, scale)
     return nv.torch_ops().mask_istft(spec, mask, int(length), n_fft, hop, win_length, float(scale), nv.MASK_MODES[mode],
                                      bool(pre_tanh))
@@ -403,6 +417,11 @@ def register_window(values):
     if wid <= 0:
         nv.check(wid)
     return int(wid)
+
+
+def conv_is_tuned(win_len, win_inc, fft_len):
+    """DCCRN's 400/100/512 family has fused kernels; other geometries run on the general path."""
+    return bool(nv.lib().se_conv_geometry_tuned(int(win_len), int(win_inc), int(fft_len)))
 
 
 def conv_stft_rows(x, win_len, win_inc, fft_len, window_id=0):

@@ -113,6 +113,45 @@ def gen_conv():
     save("conv_polar", x=x, mags=mags, phase=phase, y=ist(mags, phase), meta=np.array([400, 100, 512, -1]))
 
 
+def gen_general_geometry():
+    """The reference's helpers and DCCRN transforms at geometries its configs do not use (any n_fft / hop / win_length is
+    accepted by torch.stft; any win_len / win_inc / fft_len by ConvSTFT): pins the general-geometry kernel path."""
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    metas = []
+    for i, (N, n, h, w) in enumerate(((1500, 256, 64, 256), (2400, 512, 160, 400), (1777, 512, 100, 512), (5000, 4096, 1024, 4096),
+                                      (700, 64, 16, 64), (3000, 2048, 300, 1200))):
+        c = cfg(n, h, w)
+        x = torch.randn(2, 1, N, generator=g, requires_grad=True)
+        spec = stft_custom(x, c)
+        gspec = torch.randn(spec.shape, generator=g)
+        (gx,) = torch.autograd.grad(spec, x, gspec)
+        s = (spec.detach() + 0.01 * torch.randn(spec.shape, generator=g)).requires_grad_(True)
+        y = istft_custom(s, N, c)
+        gy = torch.randn(y.shape, generator=g)
+        (gs,) = torch.autograd.grad(y, s, gy)
+        for k, v in (("x", x), ("spec", spec), ("gspec", gspec), ("gx", gx), ("s", s), ("y", y), ("gy", gy), ("gs", gs)):
+            out[f"t{i}_{k}"] = v
+        metas.append([N, n, h, w])
+    out["t_meta"] = np.array(metas)
+    metas = []
+    for i, (N, wl, inc, nfft, wt) in enumerate(((1600, 320, 160, 512, "hann"), (2000, 400, 100, 1024, "hamming"),
+                                                (1200, 256, 64, 256, "hann"), (1700, 400, 128, 512, "hamming"))):
+        x = torch.randn(2, 1, N, generator=g)
+        st = ConvSTFT(wl, inc, nfft, wt, "complex")
+        ist = ConviSTFT(wl, inc, nfft, None, wt, "complex")
+        spec = st(x)
+        s = (spec + 0.05 * torch.randn(spec.shape, generator=g)).detach().requires_grad_(True)
+        y = ist(s)
+        gy = torch.randn(y.shape, generator=g)
+        (gs,) = torch.autograd.grad(y, s, gy)
+        for k, v in (("x", x), ("spec", spec), ("s", s), ("y", y), ("gy", gy), ("gs", gs)):
+            out[f"c{i}_{k}"] = v
+        metas.append([N, wl, inc, nfft, 0 if wt == "hann" else 1])
+    out["c_meta"] = np.array(metas)
+    save("general_geometry", **out)
+
+
 def gen_dccrn_masks():
     """Capture (specs, mask, masked spec, wav) from real DCCRN forwards for E / C / R."""
     torch.manual_seed(3)
@@ -325,6 +364,9 @@ def gen_losses_evaluate_collate_features():
 
 
 if __name__ == "__main__":
+    if "--only-general" in sys.argv:
+        gen_general_geometry()
+        sys.exit(0)
     if "--only-f-rows" in sys.argv:
         gen_losses_evaluate_collate_features()
         sys.exit(0)
@@ -338,3 +380,4 @@ if __name__ == "__main__":
     gen_dccrn_masks()
     gen_dcunet_mask()
     gen_segments()
+    gen_general_geometry()

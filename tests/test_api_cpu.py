@@ -28,7 +28,9 @@ def test_unsupported_configs_raise_not_fallback():
     with pytest.raises(NotImplementedError):
         se.stft_custom(x, cfg(320, 80, 320))          # commented CRN setting, src/conf/config.yaml:78-80
     with pytest.raises(NotImplementedError):
-        se.stft_custom(x, cfg(512, 100, 512))
+        se.stft_custom(x, cfg(512, 600, 512))         # hop > n_fft
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.stft_custom(x, cfg(512, 100, 512))         # a general geometry is built -- but there is still no CPU path
     with pytest.raises(NotImplementedError):
         se.stft_custom(x, cfg(center=False))
     with pytest.raises(ValueError):
@@ -83,7 +85,9 @@ def test_fused_tail_and_tasnet_entry_points_validate_without_a_gpu():
     with pytest.raises(RuntimeError):
         se.apply_mask_istft(torch.randn(1, 1, 129, 33, 2), torch.randn(1, 1, 129, 33, 2), 4096, cfg(), "C")
     with pytest.raises(NotImplementedError):
-        se.apply_mask_istft(spec, mask, 4096, cfg(512, 100, 512), "C")
+        se.apply_mask_istft(spec, mask, 4096, cfg(512, 600, 512), "C")         # hop > n_fft
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.apply_mask_istft(spec, mask, 4096, cfg(512, 100, 512), "C")        # general geometry: two stages, still CUDA-only
     with pytest.raises(RuntimeError, match="CUDA"):
         se.overlap_and_add(torch.randn(2, 5, 40), 20)
     with pytest.raises(ValueError):

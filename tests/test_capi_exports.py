@@ -45,7 +45,11 @@ def test_argument_errors_do_not_need_a_gpu():
     buf = (ctypes.c_float * 4)()
     p = ctypes.cast(buf, ctypes.c_void_p)
     assert L.se_stft_fwd(p, p, 1, 4096, 320, 80, 320, 1.0, None) == -2          # n_fft=320: clear error, no fallback
-    assert L.se_stft_fwd(p, p, 1, 4096, 512, 100, 512, 1.0, None) == -2
+    assert L.se_stft_fwd(p, p, 1, 4096, 512, 600, 512, 1.0, None) == -2          # hop > n_fft
+    assert L.se_stft_fwd(p, p, 1, 100, 512, 100, 512, 1.0, None) == -1           # general geometry: reflect padding needs N > n/2
+    assert L.se_geometry_tuned(512, 128) == 1 and L.se_geometry_tuned(512, 100) == 0 and L.se_geometry_tuned(256, 64) == 0
+    assert L.se_conv_geometry_tuned(400, 100, 512) == 1 and L.se_conv_geometry_tuned(320, 160, 512) == 0
+    assert L.se_enhance_fwd(p, p, p, 1, 4096, 256, 64, 256, 1, 0, None) == -2     # fused ops: tuned geometries only
     assert L.se_istft_fwd(p, p, 1, 0, 100, 512, 128, 512, 1.0, None) == -1
     assert L.se_mask_fwd(p, p, p, 4, 7, 0, None) == -2
 
@@ -57,7 +61,7 @@ def test_torch_extension_registers_the_operators():
     import torch
     from speech_enhancement_pytorch_b200 import _native as nv
     ops = nv.torch_ops()
-    for name in ("stft", "istft", "mask", "mask_istft", "enhance", "mrstft_loss"):
+    for name in ("stft", "istft", "mask", "mask_istft", "enhance", "mrstft_loss", "conv_stft", "conv_istft", "conv_mask_istft"):
         assert hasattr(ops, name), name
     assert "Tensor x, int n_fft, int hop, int win_length, float scale" in str(torch.ops.se_b200.stft.default._schema)
     with pytest.raises(RuntimeError, match="CUDA"):
