@@ -46,9 +46,9 @@ int se_version(void);
 const char* se_last_error(void);
 
 /* ---- geometries.  The tuned engine is compiled for n_fft 512 / 1024 / 2048 at hop n_fft/4 or n_fft/2 (and DCCRN's
- * ConvSTFT / ConviSTFT 400/100/512); every other geometry the reference's signatures accept -- any power-of-two n_fft in
- * 8 .. 8192, any 1 <= hop <= n_fft, any win_length <= n_fft; any win_len / win_inc / power-of-two fft_len for the DCCRN
- * transforms -- runs on the general path (csrc/se_generic.cuh) behind the SAME entry points: se_stft_fwd / se_stft_bwd /
+ * ConvSTFT / ConviSTFT 400/100/512); every other geometry the reference's signatures accept -- any even n_fft in
+ * 8 .. 8192 (not a power of two: Bluestein), any 1 <= hop <= n_fft, any win_length <= n_fft; any win_len / win_inc /
+ * even fft_len for the DCCRN transforms -- runs on the general path (csrc/se_generic.cuh) behind the SAME entry points: se_stft_fwd / se_stft_bwd /
  * se_istft_fwd / se_istft_bwd and se_conv_stft_fwd_w / se_conv_istft_fwd_w / se_conv_istft_bwd_w.  The fused entry
  * points (enhance, mask_istft, conv_mask_istft, the losses, the segment transforms) exist for tuned geometries only;
  * the host side composes them from the plain transforms otherwise.  These two report which case applies (1 = tuned). */

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 namespace se {
@@ -19,8 +20,7 @@ bool geometry_tuned(int n_fft, int hop) {
 
 int check_general(int64_t rows, int64_t nsample, int n_fft, int hop, int win_length) {
     if (rows <= 0 || nsample <= 0) return fail(SE_ERR_BAD_ARG, "rows and nsample must be positive");
-    if (n_fft < 8 || n_fft > 8192 || (n_fft & (n_fft - 1)))
-        return fail(SE_ERR_UNSUPPORTED, "n_fft must be a power of two in 8 .. 8192");
+    if (n_fft < 8 || n_fft > 8192 || (n_fft & 1)) return fail(SE_ERR_UNSUPPORTED, "n_fft must be even, 8 .. 8192");
     if (hop < 1 || hop > n_fft) return fail(SE_ERR_UNSUPPORTED, "need 1 <= hop_length <= n_fft");
     if (win_length < 2 || win_length > n_fft) return fail(SE_ERR_UNSUPPORTED, "need 2 <= win_length <= n_fft");
     if (nsample + 2LL * n_fft > 0x7fffffffLL || rows * (nsample / hop + 2) > 0x7fffffffLL)
@@ -39,6 +39,29 @@ struct GenKey {
 static std::mutex g_gen_mu;
 static std::map<GenKey, GenTables> g_gen_tables;
 
+// in-place radix-2 FFT (forward, e^{-i}) in double: builds the Bluestein filter spectrum once per geometry
+static void host_fft(std::vector<double>& re, std::vector<double>& im) {
+    const size_t L = re.size();
+    for (size_t i = 1, j = 0; i < L; ++i) {
+        size_t bit = L >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+    }
+    const double two_pi = 6.283185307179586476925286766559;
+    for (size_t len = 2; len <= L; len <<= 1) {
+        for (size_t i = 0; i < L; i += len) {
+            for (size_t k = 0; k < len / 2; ++k) {
+                const double ang = -two_pi * (double)k / (double)len, wr = std::cos(ang), wi = std::sin(ang);
+                const size_t a = i + k, b = i + k + len / 2;
+                const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+                re[b] = re[a] - xr; im[b] = im[a] - xi;
+                re[a] += xr; im[a] += xi;
+            }
+        }
+    }
+}
+
 static int get_gen_tables(int n, int win_len, bool front, float scale, int window_id, GenTables& out) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -53,34 +76,57 @@ static int get_gen_tables(int n, int win_len, bool front, float scale, int windo
     const int M = n / 2;
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<float> win(n), w2(n);
-    std::vector<float2> tw(M), twn(M + 1);
+    const int L = gen_bluestein_len(n);
+    const int TW = L ? L : M;                        // the FFT that runs is L-point (Bluestein) or M-point
+    std::vector<float2> tw(TW), twn(M + 1);
     for (int j = 0; j < n; ++j) {
         win[j] = (float)(w[j] * (double)scale);
         const float wf = (float)w[j];
         w2[j] = wf * wf;
     }
-    for (int k = 0; k < M; ++k) tw[k] = make_float2((float)std::cos(two_pi * k / M), (float)-std::sin(two_pi * k / M));
+    for (int k = 0; k < TW; ++k) tw[k] = make_float2((float)std::cos(two_pi * k / TW), (float)-std::sin(two_pi * k / TW));
     for (int k = 0; k <= M; ++k) twn[k] = make_float2((float)std::cos(two_pi * k / n), (float)-std::sin(two_pi * k / n));
     float *d_win = nullptr, *d_w2 = nullptr;
     float2 *d_tw = nullptr, *d_twn = nullptr;
     cudaError_t e;
     if ((e = cudaMalloc((void**)&d_win, n * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&d_w2, n * sizeof(float))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    if ((e = cudaMalloc((void**)&d_tw, M * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    if ((e = cudaMalloc((void**)&d_tw, TW * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     if ((e = cudaMalloc((void**)&d_twn, (M + 1) * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
     cudaMemcpy(d_win, win.data(), n * sizeof(float), cudaMemcpyHostToDevice);
     cudaMemcpy(d_w2, w2.data(), n * sizeof(float), cudaMemcpyHostToDevice);
-    cudaMemcpy(d_tw, tw.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tw, tw.data(), TW * sizeof(float2), cudaMemcpyHostToDevice);
     e = cudaMemcpy(d_twn, twn.data(), (M + 1) * sizeof(float2), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tables)");
-    out = GenTables{d_win, d_w2, d_tw, d_twn};
+    out = GenTables{d_win, d_w2, d_tw, d_twn, nullptr, nullptr, 0};
+    if (L) {
+        // chirp c_j = e^{i pi j^2 / M} (j^2 reduced mod 2M in integers) and the L-point FFT of the filter, in double
+        std::vector<float2> chirp(M), bf(L);
+        std::vector<double> br(L, 0.0), bi(L, 0.0);
+        for (int j = 0; j < M; ++j) {
+            const long long r = ((long long)j * j) % (2LL * M);
+            const double ang = two_pi * 0.5 * (double)r / (double)M;
+            chirp[j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+            br[j] = std::cos(ang); bi[j] = std::sin(ang);
+            if (j) { br[L - j] = br[j]; bi[L - j] = bi[j]; }
+        }
+        host_fft(br, bi);
+        for (int k = 0; k < L; ++k) bf[k] = make_float2((float)(br[k] / L), (float)(bi[k] / L));
+        float2 *d_chirp = nullptr, *d_bf = nullptr;
+        if ((e = cudaMalloc((void**)&d_chirp, M * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        if ((e = cudaMalloc((void**)&d_bf, L * sizeof(float2))) != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+        cudaMemcpy(d_chirp, chirp.data(), M * sizeof(float2), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(d_bf, bf.data(), L * sizeof(float2), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(tables)");
+        out.chirp = d_chirp; out.bfft = d_bf; out.L = L;
+    }
     g_gen_tables[key] = out;
     return 0;
 }
 
 // ------------------------------------------------------------------ launches
 static int gen_warps(int n) {
-    const size_t per_warp = gen_smem_bytes(n, 1);
+    const size_t per_warp = gen_smem_bytes(n, 1);                 // at most 128 KB (Bluestein L = 8192 for n_fft > 4097)
     size_t w = (96 * 1024) / per_warp;
     return (int)(w < 1 ? 1 : (w > 8 ? 8 : w));
 }
@@ -90,7 +136,8 @@ static int run_gen_analysis(GenArgs a, int64_t rows, cudaStream_t st, const char
     const int W = gen_warps(a.n);
     const int64_t cpr = (a.nframe + W - 1) / W;
     if (rows * cpr > 0x7fffffffLL) return fail(SE_ERR_BAD_ARG, "problem too large for one launch");
-    const cudaError_t e = launch_ex(false, k_gen_analysis<LMODE>, (unsigned)(rows * cpr), 32u * W, gen_smem_bytes(a.n, W), st, a);
+    const cudaError_t e = a.tb.L ? launch_ex(false, k_gen_analysis<LMODE, true>, (unsigned)(rows * cpr), 32u * W, gen_smem_bytes(a.n, W), st, a)
+                                 : launch_ex(false, k_gen_analysis<LMODE, false>, (unsigned)(rows * cpr), 32u * W, gen_smem_bytes(a.n, W), st, a);
     return e == cudaSuccess ? 0 : cuda_fail(e, what);
 }
 
@@ -148,7 +195,8 @@ static int run_gen_synthesis(GenArgs a, int64_t rows, int64_t spec_row_floats, c
         GenArgs f = a;
         f.in = spec + r0 * spec_row_floats;
         f.out = scratch;
-        e = launch_ex(false, k_gen_frames, (unsigned)(nr * cpr), 32u * W, gen_smem_bytes(a.n, W), st, f);
+        e = a.tb.L ? launch_ex(false, k_gen_frames<true>, (unsigned)(nr * cpr), 32u * W, gen_smem_bytes(a.n, W), st, f)
+                   : launch_ex(false, k_gen_frames<false>, (unsigned)(nr * cpr), 32u * W, gen_smem_bytes(a.n, W), st, f);
         if (e != cudaSuccess) break;
         GenArgs o = a;
         o.in = scratch;
@@ -230,8 +278,8 @@ int gen_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nframe, i
 // ------------------------------------------------------------------ DCCRN convention (window at the front of the frame)
 static int conv_general_check(int64_t rows, int win_len, int win_inc, int fft_len) {
     if (rows <= 0) return fail(SE_ERR_BAD_ARG, "empty tensor");
-    if (fft_len < 8 || fft_len > 8192 || (fft_len & (fft_len - 1)))
-        return fail(SE_ERR_UNSUPPORTED, "ConvSTFT / ConviSTFT: fft_len must be a power of two in 8 .. 8192");
+    if (fft_len < 8 || fft_len > 8192 || (fft_len & 1))
+        return fail(SE_ERR_UNSUPPORTED, "ConvSTFT / ConviSTFT: fft_len must be even, 8 .. 8192");
     if (win_inc < 1 || win_len < win_inc || win_len > fft_len)
         return fail(SE_ERR_UNSUPPORTED, "ConvSTFT / ConviSTFT: need 1 <= win_inc <= win_len <= fft_len");
     return 0;

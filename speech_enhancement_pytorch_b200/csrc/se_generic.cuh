@@ -1,4 +1,6 @@
-// se_generic.cuh -- the general-geometry transform path: any power-of-two n_fft (8 .. 8192), any hop 1 .. n_fft, any
+// se_generic.cuh -- the general-geometry transform path: any power-of-two n_fft (8 .. 8192) and -- through Bluestein's
+// chirp-z over a power-of-two length -- any even n_fft up to 4096 (the reference's commented CRN setting n_fft = 320,
+// src/conf/config.yaml:78-80; the common 400-point speech front end); any hop 1 .. n_fft, any
 // win_length <= n_fft, window centred (torch.stft, src/evaluate.py:109-119) or at the front of the frame (DCCRN's
 // ConvSTFT / ConviSTFT with any win_len / win_inc / fft_len, src/model/dccrn.py:649-747).
 //
@@ -24,6 +26,11 @@ struct GenTables {
     const float* w2;      // [n] squared (unscaled, fp32-rounded) window: overlap-add envelope
     const float2* tw;     // [M] e^{-2 pi i k / M}
     const float2* twn;    // [M + 1] e^{-2 pi i k / n}
+    // n_fft not a power of two (even n): the M = n/2 point complex DFT runs as Bluestein's chirp-z over a power-of-two
+    // length L >= 2M - 1; tw is then [L]
+    const float2* chirp;  // [M] c_j = e^{+i pi j^2 / M}
+    const float2* bfft;   // [L] FFT_L of the chirp filter b (b_m = b_{L-m} = c_m, m < M), pre-divided by L
+    int L;                // 0: power-of-two path
 };
 
 struct GenArgs {
@@ -153,12 +160,55 @@ __device__ __forceinline__ void parity_correct(float2* z, int M, int lane, int p
 }
 
 // per-warp buffers: two of (M + 1) float2, padded to an even count of float2 (16-byte aligned rows)
-__host__ __device__ inline int gen_buf_len(int n) { return (n / 2 + 2) & ~1; }
+// Bluestein length for n_fft that is not a power of two (0 for powers of two): power of two >= 2 (n/2) - 1
+__host__ __device__ inline int gen_bluestein_len(int n) {
+    if ((n & (n - 1)) == 0) return 0;
+    int L = 1;
+    while (L < n - 1) L <<= 1;
+    return L;
+}
+__host__ __device__ inline int gen_buf_len(int n) {
+    const int L = gen_bluestein_len(n);
+    return L ? L : ((n / 2 + 2) & ~1);            // L >= n - 1 >= n/2 + 1 entries for the bins
+}
 inline size_t gen_smem_bytes(int n, int warps) { return (size_t)warps * 2 * gen_buf_len(n) * sizeof(float2); }
 
 // ------------------------------------------------------------------ analysis: waveform-like -> spectrum
 // grid = rows x ceil(T / W), block = 32 W
-template <int LMODE>
+// M-point complex DFT of x (forward e^{-i}, inverse e^{+i}, unnormalised); returns the buffer holding the result.
+// BZ = false: M is a power of two, Stockham FFT.  BZ = true: Bluestein -- the DFT as a circular convolution of length
+// L >= 2M - 1 with the chirp c_j = e^{i pi j^2 / M}: X_k = conj(c_k) sum_j (x_j conj(c_j)) c_{k-j}; the filter's spectrum
+// (pre-divided by L) is a table, so it costs two L-point FFTs.  The inverse is conj(DFT(conj x)).  Both FFTs take the
+// same number of ping-pong passes, so the Bluestein result is always back in x.
+template <bool INV, bool BZ>
+__device__ __forceinline__ float2* gen_cdft(float2* x, float2* y, const GenTables& tb, int M, int lane) {
+    if (!BZ) return warp_fft<INV>(x, y, tb.tw, M, lane);
+    const int L = tb.L;
+    for (int j = lane; j < L; j += 32) {
+        float2 v = make_float2(0.f, 0.f);
+        if (j < M) {
+            v = x[j];
+            if (INV) v.y = -v.y;
+            v = g_mul(v, g_conj(__ldg(tb.chirp + j)));
+        }
+        x[j] = v;
+    }
+    __syncwarp();
+    float2* z = warp_fft<false>(x, y, tb.tw, L, lane);
+    float2* o = (z == x) ? y : x;
+    for (int j = lane; j < L; j += 32) z[j] = g_mul(z[j], __ldg(tb.bfft + j));
+    __syncwarp();
+    warp_fft<true>(z, o, tb.tw, L, lane);
+    for (int k = lane; k < M; k += 32) {
+        float2 v = g_mul(x[k], g_conj(__ldg(tb.chirp + k)));
+        if (INV) v.y = -v.y;
+        x[k] = v;
+    }
+    __syncwarp();
+    return x;
+}
+
+template <int LMODE, bool BZ>
 __global__ void k_gen_analysis(GenArgs a) {
     SE_SMEM_DECL;
     pdl_wait();
@@ -172,7 +222,7 @@ __global__ void k_gen_analysis(GenArgs a) {
     const int t = t0 + warp;
     const float* src = a.in + (size_t)row * a.in_stride;
     // the FFT ping-pongs once per pass: the split writes to the buffer the transform did NOT end in (same for every warp)
-    const int spec_off = (gen_fft_passes(M) & 1) ? 0 : BL;
+    const int spec_off = BZ ? BL : ((gen_fft_passes(M) & 1) ? 0 : BL);
     if (t < a.nframe) {
         const int base = t * a.hop;
         for (int m = lane; m < M; m += 32) {
@@ -184,7 +234,7 @@ __global__ void k_gen_analysis(GenArgs a) {
         }
         __syncwarp();
         if (a.parity_len > 0) parity_correct(x, M, lane, a.parity_len, a.inv_even, a.inv_odd);
-        const float2* z = warp_fft<false>(x, y, a.tb.tw, M, lane);
+        const float2* z = gen_cdft<false, BZ>(x, y, a.tb, M, lane);
         float2* o = x + spec_off;
         // real-FFT split: X[k] = 1/2 [(Z_k + conj Z_{M-k}) - i e^{-2 pi i k/n} (Z_k - conj Z_{M-k})], k = 0 .. M
         for (int k = lane; k <= M; k += 32) {
@@ -213,6 +263,7 @@ __global__ void k_gen_analysis(GenArgs a) {
 
 // ------------------------------------------------------------------ synthesis 1: spectrum -> windowed frames
 // out = scratch [rows, T, f_len]; grid = rows x ceil(T / W), block = 32 W
+template <bool BZ>
 __global__ void k_gen_frames(GenArgs a) {
     SE_SMEM_DECL;
     pdl_wait();
@@ -243,6 +294,7 @@ __global__ void k_gen_frames(GenArgs a) {
     if (t >= T) return;
     float2* x = bufs + (size_t)warp * 2 * BL;
     float2* y = x + BL;
+    float* dst = a.out + ((size_t)row * T + t) * a.f_len;
     // Z_k = (X_k + conj X_{M-k}) + i e^{+2 pi i k/n} (X_k - conj X_{M-k}); inverse FFT gives z[m] = v[2m] + i v[2m+1],
     // v[j] = X_0 + (-1)^j X_M + 2 Re sum_{0<k<M} X_k e^{+2 pi i jk/n}
     for (int k = lane; k < M; k += 32) {
@@ -252,14 +304,14 @@ __global__ void k_gen_frames(GenArgs a) {
         x[k] = make_float2(s.x - wd.y, s.y + wd.x);
     }
     __syncwarp();
-    float2* z = warp_fft<true>(x, y, a.tb.tw, M, lane);
+    float2* z = gen_cdft<true, BZ>(x, y, a.tb, M, lane);
     if (a.parity_len > 0) parity_correct(z, M, lane, a.parity_len, a.inv_even, a.inv_odd);
-    float2* dst = reinterpret_cast<float2*>(a.out + ((size_t)row * T + t) * a.f_len);
+    float2* dst2 = reinterpret_cast<float2*>(dst);
     const int m_lo = a.f_lo >> 1, m_cnt = a.f_len >> 1;
     for (int m = lane; m < m_cnt; m += 32) {
         const float2 v = z[m_lo + m];
         const int j = 2 * (m_lo + m);
-        dst[m] = make_float2(v.x * __ldg(a.tb.win + j), v.y * __ldg(a.tb.win + j + 1));
+        dst2[m] = make_float2(v.x * __ldg(a.tb.win + j), v.y * __ldg(a.tb.win + j + 1));
     }
 }
 

@@ -45,8 +45,8 @@ float* mp(Tensor& t) { return t.mutable_data_ptr<float>(); }
 
 // fused = nullptr: any geometry the general path takes; otherwise the name of a fused op built for the tuned geometries only
 void check_cfg(int64_t n_fft, int64_t hop, int64_t win, const char* fused = nullptr) {
-    TORCH_CHECK_NOT_IMPLEMENTED(n_fft >= 8 && n_fft <= 8192 && (n_fft & (n_fft - 1)) == 0, "n_fft=", n_fft,
-                                ": powers of two in 8..8192 are built (no CPU / cuFFT fallback path)");
+    TORCH_CHECK_NOT_IMPLEMENTED(n_fft >= 8 && n_fft <= 8192 && !(n_fft & 1), "n_fft=", n_fft,
+                                ": even sizes in 8..8192 are built (no CPU / cuFFT fallback path)");
     TORCH_CHECK_NOT_IMPLEMENTED(hop >= 1 && hop <= n_fft, "hop_length=", hop, " must be in [1, n_fft]");
     TORCH_CHECK_NOT_IMPLEMENTED(win >= 2 && win <= n_fft, "win_length=", win, " must be in [2, n_fft]");
     TORCH_CHECK_NOT_IMPLEMENTED(!fused || se_geometry_tuned((int)n_fft, (int)hop), fused,

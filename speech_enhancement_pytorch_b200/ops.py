@@ -24,8 +24,8 @@ def is_tuned(n_fft, hop):
 
 def _check_cfg(n_fft, hop, win_length, tuned_only=None):
     """tuned_only: name of a fused op that only exists for the tuned geometries."""
-    if n_fft < 8 or n_fft > 8192 or (n_fft & (n_fft - 1)):
-        raise NotImplementedError(f"n_fft={n_fft}: powers of two in 8..8192 are built (no CPU / cuFFT fallback path)")
+    if n_fft < 8 or n_fft > 8192 or (n_fft & 1):
+        raise NotImplementedError(f"n_fft={n_fft}: even sizes in 8..8192 are built (no CPU / cuFFT fallback path)")
     if not (1 <= hop <= n_fft):
         raise NotImplementedError(f"hop_length={hop} must be in [1, n_fft]")
     if not (2 <= win_length <= n_fft):

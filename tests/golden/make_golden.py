@@ -120,7 +120,7 @@ def gen_general_geometry():
     out = {}
     metas = []
     for i, (N, n, h, w) in enumerate(((1500, 256, 64, 256), (2400, 512, 160, 400), (1777, 512, 100, 512), (5000, 4096, 1024, 4096),
-                                      (700, 64, 16, 64), (3000, 2048, 300, 1200))):
+                                      (700, 64, 16, 64), (3000, 2048, 300, 1200), (3000, 320, 160, 320), (2222, 400, 100, 400))):
         c = cfg(n, h, w)
         x = torch.randn(2, 1, N, generator=g, requires_grad=True)
         spec = stft_custom(x, c)

@@ -26,7 +26,9 @@ def test_cpu_tensors_are_refused_loudly():
 def test_unsupported_configs_raise_not_fallback():
     x = torch.randn(1, 1, 4096)
     with pytest.raises(NotImplementedError):
-        se.stft_custom(x, cfg(320, 80, 320))          # commented CRN setting, src/conf/config.yaml:78-80
+        se.stft_custom(x, cfg(321, 80, 321))          # odd n_fft
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.stft_custom(x, cfg(320, 160, 320))         # the commented CRN setting (src/conf/config.yaml:78-80) is built, CUDA-only
     with pytest.raises(NotImplementedError):
         se.stft_custom(x, cfg(512, 600, 512))         # hop > n_fft
     with pytest.raises(RuntimeError, match="CUDA"):

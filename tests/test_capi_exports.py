@@ -44,7 +44,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert b"null" in L.se_last_error()
     buf = (ctypes.c_float * 4)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert L.se_stft_fwd(p, p, 1, 4096, 320, 80, 320, 1.0, None) == -2          # n_fft=320: clear error, no fallback
+    assert L.se_stft_fwd(p, p, 1, 4096, 321, 80, 321, 1.0, None) == -2          # odd n_fft: clear error, no fallback
     assert L.se_stft_fwd(p, p, 1, 4096, 512, 600, 512, 1.0, None) == -2          # hop > n_fft
     assert L.se_stft_fwd(p, p, 1, 100, 512, 100, 512, 1.0, None) == -1           # general geometry: reflect padding needs N > n/2
     assert L.se_geometry_tuned(512, 128) == 1 and L.se_geometry_tuned(512, 100) == 0 and L.se_geometry_tuned(256, 64) == 0
@@ -67,4 +67,4 @@ def test_torch_extension_registers_the_operators():
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.mrstft_loss(torch.zeros(1, 4096), torch.zeros(1, 4096))
     with pytest.raises(NotImplementedError):
-        ops.istft(torch.zeros(1, 161, 5, 2), 640, 320, 80, 320, 320.0)
+        ops.istft(torch.zeros(1, 161, 5, 2), 640, 321, 80, 321, 321.0)

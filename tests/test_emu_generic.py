@@ -31,7 +31,9 @@ def r2(c):
 # short windows, hop = 1 sample, rows shorter than n_fft
 CASES = [(256, 64, 256, 1500), (512, 160, 400, 2400), (512, 100, 512, 1777), (1024, 341, 1024, 4000), (4096, 1024, 4096, 9000),
          (64, 16, 64, 333), (16, 5, 16, 97), (8, 2, 8, 41), (128, 1, 128, 200), (512, 128, 512, 300), (8192, 2048, 8192, 9000),
-         (2048, 300, 1200, 5000)]
+         (2048, 300, 1200, 5000),
+         # n_fft that is not a power of two: Bluestein (the commented CRN setting 320/160, config.yaml:78-80; 400-point front ends)
+         (320, 160, 320, 3000), (400, 100, 400, 2222), (400, 160, 400, 1600), (100, 25, 100, 700), (360, 90, 300, 2000), (12, 3, 12, 50), (1000, 250, 1000, 2800), (6000, 1500, 6000, 7000), (10, 2, 10, 40)]
 
 
 @pytest.mark.parametrize("n,hop,win,N", CASES)
@@ -53,7 +55,7 @@ def test_general_geometry_transforms_vs_f64(n, hop, win, N):
     assert rel(gx2 - base, gx) < 1e-5
     if tuned:
         return                                          # N < n_fft: only the adjoint takes the general path
-    for length in (N, N - N // 7, N + 50):
+    for length in (N, N - N // 7) + ((N + 50,) if win == n else ()):
         y = E.istft_fwd(r2(spec), length, n, hop, win, float(win))
         assert not np.isnan(y).any()
         assert rel(y, o64.istft(spec.astype(np.complex64), n, hop, win, length)) < 3e-6
@@ -87,14 +89,14 @@ def test_general_geometry_envelope_error():
 
 def test_general_geometry_rejects_what_it_cannot_do():
     x = np.zeros((1, 4000), np.float32)
-    for n, hop, win in ((400, 100, 400), (512, 600, 512), (512, 128, 600), (16384, 4096, 16384)):
+    for n, hop, win in ((401, 100, 401), (512, 600, 512), (512, 128, 600), (16384, 4096, 16384)):
         with pytest.raises(RuntimeError):
             E.stft_fwd(x, n, hop, win, 1.0)
 
 
 # (win_len, win_inc, fft_len): the reference's ConvSTFT / ConviSTFT take any of these (dccrn.py:669-747)
 CONV_CASES = [(320, 160, 512), (512, 128, 512), (400, 100, 1024), (256, 64, 256), (25, 10, 32), (400, 160, 512), (401, 100, 512),
-              (400, 128, 512)]
+              (400, 128, 512), (400, 100, 400), (300, 75, 360)]
 
 
 @pytest.mark.parametrize("wl,inc,nfft", CONV_CASES)

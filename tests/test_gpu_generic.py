@@ -72,7 +72,7 @@ def test_reference_run_goldens_dccrn_convention(se):
 
 @pytest.mark.parametrize("n,hop,win,N,rows", [(256, 64, 256, 16000, 8), (512, 160, 400, 16000, 8), (4096, 1024, 4096, 40000, 3),
                                               (8192, 2048, 8192, 50000, 2), (1024, 100, 1024, 9000, 4), (128, 32, 128, 5000, 5),
-                                              (512, 128, 512, 300, 3)])
+                                              (512, 128, 512, 300, 3), (320, 160, 320, 16000, 8), (400, 100, 400, 16000, 8), (1000, 250, 800, 9000, 3)])
 def test_seeded_vs_oracle(se, oref, n, hop, win, N, rows):
     c = cfg(n, hop, win)
     x = torch.randn(rows, 1, N, generator=torch.Generator().manual_seed(n + hop))
@@ -130,7 +130,7 @@ def test_dccrn_general_geometry_tail_and_errors(se, oref):
     y.sum().backward()
     assert torch.isfinite(mre.grad).all() and torch.isfinite(mim.grad).all()
     with pytest.raises((NotImplementedError, RuntimeError)):
-        se.stft_custom(x, cfg(400, 100, 400))                # not a power of two
+        se.stft_custom(x, cfg(401, 100, 401))                # odd n_fft
     with pytest.raises(RuntimeError, match="overlap add"):
         se.istft_custom(torch.zeros(1, 1, 129, 5, 2).cuda(), 900, cfg(256, 256, 256))
 
