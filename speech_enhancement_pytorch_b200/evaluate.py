@@ -203,7 +203,8 @@ def evaluate(mixture, model, device, config):
         nbatch, nchannel, length = x.shape
         name = config.model.name
         multi = bool(model) and name in MULTI_SPEECH_SEPERATION_MODELS
-        if name in STFT_MODELS:
+        n_fft, hop, _ = _cfg(config.model) if name in STFT_MODELS else (0, 0, 0)
+        if name in STFT_MODELS and ops.is_tuned(n_fft, hop):
             stats = row_stats(x) if norm == "z-score" else None
             batch, nseg = segment_stft(x, num_feature, stride, config.model, stats)
             if model:
@@ -218,7 +219,9 @@ def evaluate(mixture, model, device, config):
             else:
                 enhanced = enhanced.reshape(nbatch, nchannel, length)
             return enhanced.to(mixture.device)
-        # waveform models: no transform on the path -- normalise, view the segments, model, stitch
+        # waveform models: no transform on the path -- normalise, view the segments, model, stitch.  STFT models at a
+        # general geometry (no fused segment / stitch kernels) take the same route with the plain transforms around the model.
+        spectral = name in STFT_MODELS
         if norm == "z-score":
             mean = torch.mean(x, dim=-1, keepdim=True)
             std = torch.std(x, dim=-1, keepdim=True)
@@ -228,12 +231,16 @@ def evaluate(mixture, model, device, config):
         batch = xp.unfold(-1, num_feature, stride).movedim(-2, 0)             # [nseg,B,C,N] view
         nseg = batch.shape[0]
         batch = batch.reshape(nseg * nbatch, nchannel, num_feature)
+        if spectral:
+            batch = stft_custom(batch, config.model)
         if model:
             model.eval()
             half = int(batch.shape[0] // 2)
             output = torch.cat([model(batch[:half]), model(batch[half:])], dim=0)
         else:
             output = batch
+        if spectral:
+            output = istft_custom(output, num_feature, config.model)
         if name in MONARCH_SPEECH_SEPARTAION_MODELS:
             output = torch.unsqueeze(output, dim=1)
         if multi:

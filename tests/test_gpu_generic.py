@@ -143,3 +143,25 @@ def test_general_geometry_large_batch_timing_sanity(se):
     spec = se.stft_custom(x, c)
     y = se.istft_custom(spec, 64000, c)
     assert rel(y, x) < TOL
+
+
+@pytest.mark.parametrize("model", [None, "mask"])
+def test_evaluate_at_a_general_geometry(se, oref, model):
+    """evaluate() (src/evaluate.py:10-98) with the commented CRN setting n_fft 320 / hop 160 (config.yaml:78-80): no fused
+    segment / stitch kernels there, the plain general-geometry transforms run around the model."""
+    g = torch.Generator().manual_seed(21)
+    mix = torch.randn(1, 2, 30000, generator=g) * 0.3 + 0.05
+    config = types.SimpleNamespace(
+        dset=types.SimpleNamespace(norm="z-score", sample_rate=16000),
+        model=types.SimpleNamespace(name="crn", segment=0.5, n_fft=320, hop_length=160, win_length=320, center=True))
+    fn = None
+    if model:
+        class Toy(torch.nn.Module):
+            def forward(self, spec):
+                f = torch.linspace(0.2, 1.0, spec.shape[-3], device=spec.device)[:, None, None]
+                return spec * f
+        fn = Toy()
+    want = oref.evaluate_ref(mix, fn, config)
+    got = se.evaluate(mix, fn.cuda() if fn else None, "cuda", config)
+    assert got.shape == want.shape
+    assert rel(got, want) < TOL
