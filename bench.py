@@ -319,6 +319,18 @@ def run_configs(se, dev, world, group, hbm_peak, fp32_peak):
     entry("cfg5_evaluate_16k", "se.evaluate(model=None): one 30 s stereo clip at 16 kHz per GPU, 814 segments x 4 s at stride 512 "
           "(row stats, shared-frame segment STFT, stitching iSTFT)", us, 30, 2 * 4 * 480000 * 2 + 8 * 257 * 501 * 814 * 2,
           channel_s_per_s=round(60 * world / us * 1e6))
+    del sets
+    # ---- general-geometry tier (csrc/se_generic.cuh): geometries outside the reference's configs, drop-in transforms only.
+    # Reported for completeness; nothing else in this line is measured on it.
+    for n, h in ((1024, 255), (320, 160)):
+        c = cfg(n, h)
+        F, T = n // 2 + 1, 1 + N // h
+        sets = [(torch.randn(64, 1, N, generator=g).to(dev),) for _ in range(2)]
+        with torch.no_grad():
+            us = timed(lambda s: se.istft_custom(se.stft_custom(s[0], c), N, c), sets, reps=10, warm=3)
+        entry(f"general_{n}_{h}", f"general-geometry tier: 64x4 s, n_fft {n} hop {h}, stft_custom -> istft_custom, no-grad", us, 256,
+              64 * (2 * S + 2 * 8 * F * T))
+        del sets
     return out
 
 

@@ -5,6 +5,7 @@
 #include "se_generic.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -177,7 +178,10 @@ static int run_gen_synthesis(GenArgs a, int64_t rows, int64_t spec_row_floats, c
     const int W = gen_warps(a.n);
     const int64_t cpr = (a.nframe + W - 1) / W;
     const int64_t frame_floats = (int64_t)a.nframe * a.f_len;
-    int64_t batch = (int64_t)(1LL << 29) / (frame_floats > 0 ? frame_floats : 1);      // <= 2 GiB of scratch
+    // <= 2 GiB of scratch (SE_GEN_SCRATCH_FLOATS overrides the cap: tests force the row-batch loop on tiny inputs)
+    const char* cap_env = std::getenv("SE_GEN_SCRATCH_FLOATS");
+    const int64_t cap = cap_env ? std::atoll(cap_env) : (int64_t)(1LL << 29);
+    int64_t batch = cap / (frame_floats > 0 ? frame_floats : 1);
     batch = batch < 1 ? 1 : (batch > rows ? rows : batch);
     if (batch > 65535) batch = 65535;                                                  // gridDim.y
     if (batch * cpr > 0x7fffffffLL) batch = 0x7fffffffLL / cpr;

@@ -708,6 +708,10 @@ static __global__ void SE_CLUSTER_DIMS(kStatsCluster) __launch_bounds__(1024) k_
     __shared__ double parts[2][kStatsCluster];
     pdl_launch_dependents();
     pdl_wait();
+#ifndef SE_EMULATE
+    // a CTA may only write a peer's shared memory once that peer has started: arrive now, wait right before the stores
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#endif
     const int rowi = blockIdx.x / kStatsCluster, part = blockIdx.x % kStatsCluster;
     const float* row = x + (size_t)rowi * row_stride;
     double s1 = 0.0, s2 = 0.0;
@@ -740,6 +744,9 @@ static __global__ void SE_CLUSTER_DIMS(kStatsCluster) __launch_bounds__(1024) k_
     }
     if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s1; sh[1][threadIdx.x >> 5] = s2; }
     __syncthreads();
+#ifndef SE_EMULATE
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");          // every CTA of the cluster is running
+#endif
     if (threadIdx.x == 0) {
         double a = 0.0, b = 0.0;
         for (int w = 0; w < 32; ++w) { a += sh[0][w]; b += sh[1][w]; }

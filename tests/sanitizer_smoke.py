@@ -33,6 +33,22 @@ def main():
         tgt = torch.randn(2, 1, N, device=dev)
         e = spec.detach().clone().requires_grad_(True)
         se.loss_spectral(e, tgt, c, "mse").backward()
+    # general-geometry path (csrc/se_generic.cuh): power-of-two and Bluestein sizes, hops that do not divide n_fft,
+    # rows shorter than n_fft, the DCCRN convention with its pinv parity correction
+    for n, h, w, N in ((256, 64, 256, 1500), (512, 160, 400, 2400), (4096, 1024, 4096, 5000), (320, 160, 320, 3000),
+                       (400, 100, 400, 2222), (64, 16, 64, 333), (512, 128, 512, 300)):
+        c = types.SimpleNamespace(n_fft=n, hop_length=h, win_length=w, center=True)
+        x = torch.randn(3, 1, N, device=dev, requires_grad=True)
+        spec = se.stft_custom(x, c)
+        m = torch.randn(*spec.shape, device=dev, requires_grad=True)
+        se.istft_custom(se.apply_mask(spec, m, "C"), N, c).sum().backward()
+        se.enhance(x.detach(), m, c, "E", True).square().mean().backward()
+    for wl, inc, nf in ((320, 160, 512), (400, 100, 1024), (300, 75, 360)):
+        gst, gist = se.ConvSTFT(wl, inc, nf, "hamming", "complex"), se.ConviSTFT(wl, inc, nf, None, "hamming", "complex")
+        gs = gst(torch.randn(2, 1, 3000, device=dev)).requires_grad_(True)
+        gist(gs).sum().backward()
+        mre, mim = (torch.randn(2, nf // 2 + 1, gs.shape[-1], device=dev, requires_grad=True) for _ in range(2))
+        gist.forward_masked(gs.detach(), mre, mim, "E").square().sum().backward()
     est = torch.randn(3, 1, 7000, device=dev, requires_grad=True)
     ref = torch.randn(3, 1, 7000, device=dev)
     se.loss_mrstft(est, ref).backward()

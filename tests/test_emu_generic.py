@@ -163,3 +163,17 @@ def test_general_geometry_matches_reference_run_goldens():
         y = k("y")[:, 0]
         assert rel(E.conv_istft_fwd_w(k("s"), y.shape[-1], wl, inc, nfft, wid), y) < 1e-4
         assert rel(E.conv_istft_bwd_w(np.ascontiguousarray(k("gy")[:, 0]), k("s").shape[-1], wl, inc, nfft, wid), k("gs")) < 1e-4
+
+
+def test_general_geometry_row_batches(monkeypatch):
+    """Synthesis scratch is bounded by processing rows in batches; force batches of one and two rows."""
+    rng = np.random.default_rng(8)
+    n, hop, win, N = 256, 50, 256, 1300
+    T, F = 1 + N // hop, n // 2 + 1
+    spec = rng.standard_normal((5, F, T)) + 1j * rng.standard_normal((5, F, T))
+    want_y = o64.istft(spec.astype(np.complex64), n, hop, win, N)
+    want_g = o64.stft_adjoint(spec, N, n, hop, win)
+    for cap in (T * n, 2 * T * n + 5):
+        monkeypatch.setenv("SE_GEN_SCRATCH_FLOATS", str(cap))
+        assert rel(E.istft_fwd(r2(spec), N, n, hop, win, float(win)), want_y) < 3e-6
+        assert rel(E.stft_bwd(r2(spec), N, n, hop, win, 1.0 / win), want_g) < 3e-6
