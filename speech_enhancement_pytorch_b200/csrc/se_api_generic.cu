@@ -128,8 +128,10 @@ static int get_gen_tables(int n, int win_len, bool front, float scale, int windo
 // ------------------------------------------------------------------ launches
 static int gen_warps(int n) {
     const size_t per_warp = gen_smem_bytes(n, 1);                 // at most 128 KB (Bluestein L = 8192 for n_fft > 4097)
-    size_t w = (96 * 1024) / per_warp;
-    return (int)(w < 1 ? 1 : (w > 8 ? 8 : w));
+    const size_t fit = (96 * 1024) / per_warp;
+    int w = 8;                                                    // a power of two: the kernels index frames with shifts
+    while (w > 1 && (size_t)w > fit) w >>= 1;
+    return w;
 }
 
 template <int LMODE>

@@ -225,12 +225,23 @@ __global__ void k_gen_analysis(GenArgs a) {
     const int spec_off = BZ ? BL : ((gen_fft_passes(M) & 1) ? 0 : BL);
     if (t < a.nframe) {
         const int base = t * a.hop;
-        for (int m = lane; m < M; m += 32) {
-            const float w0 = __ldg(a.tb.win + 2 * m), w1 = __ldg(a.tb.win + 2 * m + 1);
-            // zero-window samples are never fetched (front windows: win_len < n)
-            const float v0 = w0 != 0.f ? gen_sample<LMODE>(a, src, base + 2 * m) * w0 : 0.f;
-            const float v1 = w1 != 0.f ? gen_sample<LMODE>(a, src, base + 2 * m + 1) * w1 : 0.f;
-            x[m] = make_float2(v0, v1);
+        // frames that lie inside the row need no reflection / zero logic per sample
+        const bool interior = LMODE != GEN_ENV && base - a.pad >= 0 && base - a.pad + n <= a.in_len;
+        if (interior) {
+            const float* f = src + (base - a.pad);
+            const float2* w2p = reinterpret_cast<const float2*>(a.tb.win);
+            for (int m = lane; m < M; m += 32) {
+                const float2 w = __ldg(w2p + m);
+                x[m] = make_float2(__ldg(f + 2 * m) * w.x, __ldg(f + 2 * m + 1) * w.y);
+            }
+        } else {
+            for (int m = lane; m < M; m += 32) {
+                const float w0 = __ldg(a.tb.win + 2 * m), w1 = __ldg(a.tb.win + 2 * m + 1);
+                // zero-window samples are never fetched (front windows: win_len < n)
+                const float v0 = w0 != 0.f ? gen_sample<LMODE>(a, src, base + 2 * m) * w0 : 0.f;
+                const float v1 = w1 != 0.f ? gen_sample<LMODE>(a, src, base + 2 * m + 1) * w1 : 0.f;
+                x[m] = make_float2(v0, v1);
+            }
         }
         __syncwarp();
         if (a.parity_len > 0) parity_correct(x, M, lane, a.parity_len, a.inv_even, a.inv_odd);
@@ -247,8 +258,9 @@ __global__ void k_gen_analysis(GenArgs a) {
     }
     __syncthreads();
     const int F = M + 1, T = a.nframe;
+    const int lw = (W > 4) ? 3 : (W > 2 ? 2 : W - 1);             // log2 W: W is 1, 2, 4 or 8 (gen_warps)
     for (int e = threadIdx.x; e < F * W; e += blockDim.x) {
-        const int w = e % W, k = e / W, tt = t0 + w;
+        const int w = e & (W - 1), k = e >> lw, tt = t0 + w;
         if (tt >= T) continue;
         const float2 v = bufs[(size_t)w * 2 * BL + spec_off + k];
         if (a.planar) {
@@ -274,8 +286,9 @@ __global__ void k_gen_frames(GenArgs a) {
     float2* bufs = reinterpret_cast<float2*>(se_smem);
     const int F = M + 1, T = a.nframe;
     // bins of W frames, frame index fastest in memory; lands in each warp's second buffer
+    const int lw = (W > 4) ? 3 : (W > 2 ? 2 : W - 1);             // log2 W: W is 1, 2, 4 or 8 (gen_warps)
     for (int e = threadIdx.x; e < F * W; e += blockDim.x) {
-        const int w = e % W, k = e / W, tt = t0 + w;
+        const int w = e & (W - 1), k = e >> lw, tt = t0 + w;
         float2 v = make_float2(0.f, 0.f);
         if (tt < T) {
             if (a.planar) {
@@ -315,16 +328,28 @@ __global__ void k_gen_frames(GenArgs a) {
     }
 }
 
-// sum of the frames' contributions at natural position i
-__device__ __forceinline__ float gen_ola_at(const GenArgs& a, const float* __restrict__ frames, int i) {
+// Overlap-add and envelope at natural position i, walking the covering frames once for both.
+// The envelope sums w2 over EVERY frame covering i; the signal only over the stored support [f_lo, f_lo + f_len) --
+// outside it the window (and so the frame) is zero, so one loop over the support frames serves both.
+__device__ __forceinline__ void gen_ola_env_at(const GenArgs& a, const float* __restrict__ frames, int i, bool want_env,
+                                               float& acc, float& env) {
     const int T = a.nframe, hop = a.hop;
-    if (i < a.f_lo) return 0.f;
+    acc = 0.f;
+    env = 0.f;
+    if (i < a.f_lo) return;
     int t_hi = (i - a.f_lo) / hop;
     t_hi = t_hi < T - 1 ? t_hi : T - 1;
     int t_lo = i - a.f_lo - a.f_len + 1;
     t_lo = t_lo <= 0 ? 0 : (t_lo + hop - 1) / hop;
-    float acc = 0.f;
-    for (int t = t_hi; t >= t_lo; --t) acc += __ldg(frames + (size_t)t * a.f_len + (i - a.f_lo - t * hop));
+    for (int t = t_hi; t >= t_lo; --t) {
+        const int j = i - t * hop;
+        acc += __ldg(frames + (size_t)t * a.f_len + (j - a.f_lo));
+        if (want_env) env += __ldg(a.tb.w2 + j);
+    }
+}
+__device__ __forceinline__ float gen_ola_at(const GenArgs& a, const float* __restrict__ frames, int i) {
+    float acc, env;
+    gen_ola_env_at(a, frames, i, false, acc, env);
     return acc;
 }
 
@@ -342,8 +367,13 @@ __global__ void k_gen_ola(GenArgs a) {
     if (EMODE == GEN_OLA_ISTFT) {
         const int i = s + a.pad;
         const int natural = a.n + a.hop * (a.nframe - 1);
-        if (i >= natural) v = 0.f;                                  // `length` beyond the signal: zeros (torch.istft pads)
-        else v = gen_ola_at(a, frames, i) / (gen_env_at(a.tb.w2, a.n, a.hop, a.nframe, i) + a.env_eps);
+        if (i >= natural) {
+            v = 0.f;                                                // `length` beyond the signal: zeros (torch.istft pads)
+        } else {
+            float acc, env;
+            gen_ola_env_at(a, frames, i, true, acc, env);           // w2 is zero outside the support: same sum as gen_env_at
+            v = acc / (env + a.env_eps);
+        }
     } else {
         // adjoint of the reflect padding: sample s receives its own position and its mirror images
         const int N = a.nsample, pad = a.pad;
