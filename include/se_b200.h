@@ -53,6 +53,14 @@ const char* se_last_error(void);
  * points (enhance, mask_istft, conv_mask_istft, the losses, the segment transforms) exist for tuned geometries only;
  * the host side composes them from the plain transforms otherwise.  These two report which case applies (1 = tuned). */
 int se_geometry_tuned(int n_fft, int hop);
+/* config.center = False (src/evaluate.py:116): torch.stft without padding, frame t = x[t hop : t hop + n_fft],
+ * T = 1 + (N - n_fft) / hop; x [rows,N] -> spec [rows,F,T,2], and its adjoint.  General-geometry kernels for every size.
+ * (istft_custom with center=False raises in the reference -- a Hann window's overlap-add envelope is zero at the first
+ * sample -- and raises here.) */
+int se_stft_nocenter_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
+                         float scale, void* stream);
+int se_stft_nocenter_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
+                         float scale, int accumulate, void* stream);
 int se_conv_geometry_tuned(int win_len, int win_inc, int fft_len);
 
 /* ---- replaces torch.stft inside stft_custom(tensor, config), src/evaluate.py:101-128 --------

@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = (
-    "se_version", "se_last_error", "se_geometry_tuned", "se_conv_geometry_tuned", "se_stft_fwd", "se_stft_segments_fwd", "se_row_stats", "se_stft_segments_norm_fwd", "se_istft_stitch_fwd",
+    "se_version", "se_last_error", "se_geometry_tuned", "se_conv_geometry_tuned", "se_stft_nocenter_fwd", "se_stft_nocenter_bwd", "se_stft_fwd", "se_stft_segments_fwd", "se_row_stats", "se_stft_segments_norm_fwd", "se_istft_stitch_fwd",
     "se_stft_segments_scratch_bytes", "se_stft_segments_shared_fwd", "se_magnitude_feature", "se_stft_feature_fwd", "se_stft_bwd", "se_istft_fwd", "se_istft_bwd",
     "se_mask_fwd", "se_mask_bwd", "se_mrstft_workspace_bytes", "se_mrstft_loss_fwd",
     "se_mrstft_loss_value", "se_mrstft_loss_bwd", "se_spectral_loss_workspace_bytes", "se_spectral_loss_fwd",

@@ -255,6 +255,31 @@ int gen_stft_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, i
     return run_gen_synthesis<GEN_OLA_ADJ>(a, rows, (int64_t)(n_fft / 2 + 1) * a.nframe * 2, st, "se_stft_bwd (general geometry) launch");
 }
 
+// center=False (torch.stft without padding, src/evaluate.py:116 passes config.center): frame t is x[t hop : t hop + n_fft]
+int gen_stft_nocenter_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
+                          float scale, cudaStream_t st) {
+    if (int rc = check_general(rows, nsample, n_fft, hop, win_length)) return rc;
+    if (nsample < n_fft) return fail(SE_ERR_BAD_ARG, "center=False needs nsample >= n_fft");
+    GenArgs a{};
+    if (int rc = get_gen_tables(n_fft, win_length, false, scale, 0, a.tb)) return rc;
+    a.in = x; a.out = spec; a.n = n_fft; a.hop = hop; a.nframe = (int)(1 + (nsample - n_fft) / hop);
+    a.in_stride = nsample; a.in_len = (int)nsample; a.pad = 0; a.edge_w = a.mid_w = 1.0f;
+    return run_gen_analysis<GEN_ZEROPAD>(a, rows, st, "se_stft_nocenter_fwd launch");
+}
+
+int gen_stft_nocenter_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
+                          float scale, int accumulate, cudaStream_t st) {
+    if (int rc = check_general(rows, nsample, n_fft, hop, win_length)) return rc;
+    if (nsample < n_fft) return fail(SE_ERR_BAD_ARG, "center=False needs nsample >= n_fft");
+    GenArgs a{};
+    if (int rc = get_gen_tables(n_fft, win_length, false, scale, 0, a.tb)) return rc;
+    a.in = gspec; a.out = gx; a.n = n_fft; a.hop = hop; a.nframe = (int)(1 + (nsample - n_fft) / hop);
+    a.pad = 0; a.edge_w = 1.0f; a.mid_w = 0.5f;                  // no padding: the reflect fold of the adjoint is empty
+    support(n_fft, win_length, false, a.f_lo, a.f_len);
+    a.out_len = (int)nsample; a.nsample = (int)nsample; a.accumulate = accumulate;
+    return run_gen_synthesis<GEN_OLA_ADJ>(a, rows, (int64_t)(n_fft / 2 + 1) * a.nframe * 2, st, "se_stft_nocenter_bwd launch");
+}
+
 int gen_istft_fwd(const float* spec, float* y, int64_t rows, int64_t nframe, int64_t length, int n_fft, int hop, int win_length,
                   float scale, cudaStream_t st) {
     if (nframe <= 0 || length <= 0) return fail(SE_ERR_BAD_ARG, "nframe and length must be positive");
@@ -343,6 +368,16 @@ int gen_conv_istft_bwd(const float* gy, float* gspec, int64_t rows, int64_t nfra
 
 }  // namespace se
 
+extern "C" int se_stft_nocenter_fwd(const float* x, float* spec, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
+                                    float scale, void* stream) {
+    if (!x || !spec) return se::fail(SE_ERR_BAD_ARG, "null pointer");
+    return se::gen_stft_nocenter_fwd(x, spec, rows, nsample, n_fft, hop, win_length, scale, (cudaStream_t)stream);
+}
+extern "C" int se_stft_nocenter_bwd(const float* gspec, float* gx, int64_t rows, int64_t nsample, int n_fft, int hop, int win_length,
+                                    float scale, int accumulate, void* stream) {
+    if (!gspec || !gx) return se::fail(SE_ERR_BAD_ARG, "null pointer");
+    return se::gen_stft_nocenter_bwd(gspec, gx, rows, nsample, n_fft, hop, win_length, scale, accumulate, (cudaStream_t)stream);
+}
 extern "C" int se_geometry_tuned(int n_fft, int hop) { return se::geometry_tuned(n_fft, hop) ? 1 : 0; }
 extern "C" int se_conv_geometry_tuned(int win_len, int win_inc, int fft_len) {
     return (fft_len == 512 && win_inc == 100 && win_len <= 4 * win_inc && win_len >= win_inc && !(win_len & 1)) ? 1 : 0;

@@ -95,6 +95,28 @@ struct StftFn : torch::autograd::Function<StftFn> {
                 Tensor(), Tensor()};
     }
 };
+// config.center = False: no padding, T = 1 + (N - n_fft) / hop
+struct StftNoCenterFn : torch::autograd::Function<StftNoCenterFn> {
+    static Tensor forward(AutogradContext* ctx, const Tensor& x, int64_t n_fft, int64_t hop, int64_t win, double scale) {
+        c10::cuda::CUDAGuard guard(x.device());
+        const int64_t rows = x.size(0), n = x.size(1);
+        TORCH_CHECK_VALUE(n >= n_fft, "stft (center=False): the input (", n, " samples) is shorter than n_fft = ", n_fft);
+        Tensor out = at::empty({rows, n_fft / 2 + 1, 1 + (n - n_fft) / hop, 2}, x.options());
+        check(se_stft_nocenter_fwd(cp(x), mp(out), rows, n, (int)n_fft, (int)hop, (int)win, (float)scale, stream_of(x)));
+        ctx->saved_data["cfg"] = std::vector<int64_t>{n, n_fft, hop, win};
+        ctx->saved_data["scale"] = scale;
+        return out;
+    }
+    static variable_list backward(AutogradContext* ctx, variable_list g) {
+        const auto c = ctx->saved_data["cfg"].toIntVector();
+        const Tensor gs = g[0].contiguous();
+        c10::cuda::CUDAGuard guard(gs.device());
+        Tensor gx = at::empty({gs.size(0), c[0]}, gs.options());
+        check(se_stft_nocenter_bwd(cp(gs), mp(gx), gs.size(0), c[0], (int)c[1], (int)c[2], (int)c[3],
+                                   (float)ctx->saved_data["scale"].toDouble(), 0, stream_of(gs)));
+        return {gx, Tensor(), Tensor(), Tensor(), Tensor()};
+    }
+};
 struct IstftFn : torch::autograd::Function<IstftFn> {
     static Tensor forward(AutogradContext* ctx, const Tensor& spec, int64_t length, int64_t n_fft, int64_t hop, int64_t win,
                           double scale) {
@@ -287,6 +309,12 @@ Tensor op_stft(const Tensor& x_in, int64_t n_fft, int64_t hop, int64_t win, doub
                                         : stft_raw(x, n_fft, hop, win, scale);        // inference: no autograd node
     return x_in.scalar_type() == at::kDouble ? out.to(at::kDouble) : out;
 }
+Tensor op_stft_nocenter(const Tensor& x_in, int64_t n_fft, int64_t hop, int64_t win, double scale) {
+    check_cfg(n_fft, hop, win);
+    TORCH_CHECK_VALUE(x_in.dim() == 2, "se_b200::stft_nocenter expects [rows, N]");
+    const Tensor out = StftNoCenterFn::apply(prep(x_in, "input"), n_fft, hop, win, scale);
+    return x_in.scalar_type() == at::kDouble ? out.to(at::kDouble) : out;
+}
 Tensor op_istft(const Tensor& spec_in, int64_t length, int64_t n_fft, int64_t hop, int64_t win, double scale) {
     check_cfg(n_fft, hop, win);
     TORCH_CHECK_VALUE(spec_in.dim() == 4 && spec_in.size(3) == 2, "se_b200::istft expects [rows, F, T, 2]");
@@ -332,6 +360,7 @@ Tensor op_conv_mask_istft(const Tensor& spec, const Tensor& mre, const Tensor& m
 }  // namespace
 
 TORCH_LIBRARY(se_b200, m) {
+    m.def("stft_nocenter(Tensor x, int n_fft, int hop, int win_length, float scale) -> Tensor");
     m.def("conv_stft(Tensor x, int win_len, int win_inc, int fft_len, int window_id) -> Tensor");
     m.def("conv_istft(Tensor spec, int out_len, int win_len, int win_inc, int fft_len, int window_id) -> Tensor");
     m.def("conv_mask_istft(Tensor spec, Tensor mask_re, Tensor mask_im, int out_len, int win_len, int win_inc, int fft_len, int mode, int window_id) -> Tensor");
@@ -351,6 +380,7 @@ TORCH_LIBRARY_IMPL(se_b200, CompositeImplicitAutograd, m) {
     m.impl("mask_istft", op_mask_istft);
     m.impl("enhance", op_enhance);
     m.impl("mrstft_loss", op_mrstft);
+    m.impl("stft_nocenter", op_stft_nocenter);
     m.impl("conv_stft", op_conv_stft);
     m.impl("conv_istft", op_conv_istft);
     m.impl("conv_mask_istft", op_conv_mask_istft);

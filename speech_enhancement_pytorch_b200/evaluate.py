@@ -11,10 +11,12 @@ from __future__ import annotations
 from . import ops
 
 
-def _cfg(config):
-    if not getattr(config, "center", True):
-        # the reference's own path always raises here: Hann + center=False has a zero envelope
-        raise NotImplementedError("center=False is not built (torch.istft raises for it with a Hann window)")
+def _cfg(config, allow_nocenter=False):
+    if not getattr(config, "center", True) and not allow_nocenter:
+        # the reference's own path raises here too: torch.istft checks the overlap-add envelope, which is zero at the
+        # first sample for a Hann window without centre padding (src/evaluate.py:143-152)
+        raise RuntimeError("center=False: window overlap add min < 1e-11 (torch.istft raises the same for the reference's "
+                           "Hann window); only stft_custom runs without centre padding")
     return int(config.n_fft), int(config.hop_length), int(config.win_length)
 
 
@@ -22,9 +24,12 @@ def stft_custom(tensor, config):
     """[B,C,N] or [B,S,C,N] -> [B,(S,)C,F,T,2], spectrum divided by win_length (evaluate.py:120)."""
     if tensor.dim() not in (3, 4):
         raise ValueError(f"stft_custom expects a 3-D or 4-D tensor, got {tensor.dim()}-D")
-    n_fft, hop, win = _cfg(config)
+    n_fft, hop, win = _cfg(config, allow_nocenter=True)
     lead, nsample = tuple(tensor.shape[:-1]), tensor.shape[-1]
-    spec = ops.stft(tensor.reshape(-1, nsample), n_fft, hop, win, 1.0 / win)
+    if getattr(config, "center", True):
+        spec = ops.stft(tensor.reshape(-1, nsample), n_fft, hop, win, 1.0 / win)
+    else:                                                       # torch.stft(center=False): no padding (evaluate.py:116)
+        spec = ops.stft_nocenter(tensor.reshape(-1, nsample), n_fft, hop, win, 1.0 / win)
     return spec.reshape(*lead, *spec.shape[1:])
 
 

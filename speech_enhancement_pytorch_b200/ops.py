@@ -94,6 +94,14 @@ def stft(x_rows, n_fft, hop, win_length, scale):
     return nv.torch_ops().stft(x_rows, n_fft, hop, win_length, float(scale))
 
 
+def stft_nocenter(x_rows, n_fft, hop, win_length, scale):
+    """torch.stft(center=False): frame t = x[t hop : t hop + n_fft] (general-geometry kernels for every size)."""
+    _check_cfg(n_fft, hop, win_length)
+    if x_rows.shape[-1] < n_fft:
+        raise RuntimeError(f"stft (center=False): the input ({x_rows.shape[-1]} samples) is shorter than n_fft = {n_fft}")
+    return nv.torch_ops().stft_nocenter(x_rows, n_fft, hop, win_length, float(scale))
+
+
 def istft(spec_rows, length, n_fft, hop, win_length, scale):
     return nv.torch_ops().istft(spec_rows, int(length), n_fft, hop, win_length, float(scale))
 

@@ -83,6 +83,21 @@ def stft_fwd(x, n, hop, win, scale):
     return out
 
 
+def stft_nocenter_fwd(x, n, hop, win, scale):
+    rows, N = x.shape
+    T = 1 + (N - n) // hop
+    out = np.full((rows, n // 2 + 1, T, 2), np.nan, np.float32)
+    check(lib().se_stft_nocenter_fwd(ptr(x), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win), f32(scale), None))
+    return out
+
+
+def stft_nocenter_bwd(g, N, n, hop, win, scale):
+    rows = g.shape[0]
+    out = np.full((rows, N), np.nan, np.float32)
+    check(lib().se_stft_nocenter_bwd(ptr(g), ptr(out), i64(rows), i64(N), ci(n), ci(hop), ci(win), f32(scale), ci(0), None))
+    return out
+
+
 def stft_bwd(g, N, n, hop, win, scale, accumulate=False, init=None):
     rows = g.shape[0]
     out = np.full((rows, N), np.nan, np.float32) if init is None else init.copy()

@@ -149,6 +149,23 @@ def gen_general_geometry():
             out[f"c{i}_{k}"] = v
         metas.append([N, wl, inc, nfft, 0 if wt == "hann" else 1])
     out["c_meta"] = np.array(metas)
+    # config.center = False: stft_custom passes it to torch.stft (src/evaluate.py:116); istft_custom raises for it
+    metas = []
+    for i, (N, n, h, w) in enumerate(((2000, 512, 128, 512), (3000, 320, 160, 320))):
+        c = SimpleNamespace(n_fft=n, hop_length=h, win_length=w, center=False)
+        x = torch.randn(2, 1, N, generator=g, requires_grad=True)
+        spec = stft_custom(x, c)
+        gspec = torch.randn(spec.shape, generator=g)
+        (gx,) = torch.autograd.grad(spec, x, gspec)
+        for k, v in (("x", x), ("spec", spec), ("gspec", gspec), ("gx", gx)):
+            out[f"n{i}_{k}"] = v
+        metas.append([N, n, h, w])
+        try:
+            istft_custom(spec.detach(), N, c)
+            raise AssertionError("the reference was expected to raise for center=False")
+        except RuntimeError:
+            pass
+    out["n_meta"] = np.array(metas)
     save("general_geometry", **out)
 
 

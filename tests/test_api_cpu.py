@@ -33,8 +33,10 @@ def test_unsupported_configs_raise_not_fallback():
         se.stft_custom(x, cfg(512, 600, 512))         # hop > n_fft
     with pytest.raises(RuntimeError, match="CUDA"):
         se.stft_custom(x, cfg(512, 100, 512))         # a general geometry is built -- but there is still no CPU path
-    with pytest.raises(NotImplementedError):
-        se.stft_custom(x, cfg(center=False))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        se.stft_custom(x, cfg(center=False))          # built (no padding), CUDA-only
+    with pytest.raises(RuntimeError, match="overlap add"):
+        se.istft_custom(torch.randn(1, 1, 257, 33, 2), 4096, cfg(center=False))     # the reference's torch.istft raises too
     with pytest.raises(ValueError):
         se.stft_custom(torch.randn(4096), cfg())
     with pytest.raises(ValueError):

@@ -155,6 +155,11 @@ def test_general_geometry_matches_reference_run_goldens():
         assert rel(E.stft_bwd(k("gspec"), N, n, h, w, 1.0 / w), k("gx")) < 1e-4
         assert rel(E.istft_fwd(k("s"), N, n, h, w, float(w)), k("y")) < 1e-4
         assert rel(E.istft_bwd(k("gy"), k("s").shape[2], n, h, w, float(w)), k("gs")) < 1e-4
+    for i, (N, n, h, w) in enumerate(g["n_meta"]):                      # config.center = False
+        N, n, h, w = int(N), int(n), int(h), int(w)
+        k = lambda name: np.ascontiguousarray(g[f"n{i}_{name}"][:, 0])
+        assert rel(E.stft_nocenter_fwd(k("x"), n, h, w, 1.0 / w), k("spec")) < 1e-4
+        assert rel(E.stft_nocenter_bwd(k("gspec"), N, n, h, w, 1.0 / w), k("gx")) < 1e-4
     for i, (N, wl, inc, nfft, wt) in enumerate(g["c_meta"]):
         wl, inc, nfft = int(wl), int(inc), int(nfft)
         wid = E.register_window(np.asarray(get_window("hamming" if wt else "hann", wl, fftbins=True), dtype=np.float64))
@@ -177,3 +182,18 @@ def test_general_geometry_row_batches(monkeypatch):
         monkeypatch.setenv("SE_GEN_SCRATCH_FLOATS", str(cap))
         assert rel(E.istft_fwd(r2(spec), N, n, hop, win, float(win)), want_y) < 3e-6
         assert rel(E.stft_bwd(r2(spec), N, n, hop, win, 1.0 / win), want_g) < 3e-6
+
+
+@pytest.mark.parametrize("n,hop,win,N", [(512, 128, 512, 2000), (1024, 256, 1024, 5000), (256, 100, 200, 1234), (320, 160, 320, 3000)])
+def test_stft_without_centre_padding(n, hop, win, N):
+    """config.center = False (src/evaluate.py:116): torch.stft without padding, and its gradient, against torch."""
+    x = torch.randn(2, N, generator=torch.Generator().manual_seed(n + hop), dtype=torch.float64, requires_grad=True)
+    w = torch.hann_window(win, dtype=torch.float64)
+    want = torch.view_as_real(torch.stft(x, n, hop, win, w, center=False, return_complex=True)) / win
+    got = E.stft_nocenter_fwd(np.ascontiguousarray(x.detach().numpy().astype(np.float32)), n, hop, win, 1.0 / win)
+    assert got.shape == tuple(want.shape)
+    assert rel(got, want.detach().numpy()) < 2e-6
+    g = torch.randn(want.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    (gx,) = torch.autograd.grad(want, x, g)
+    got_g = E.stft_nocenter_bwd(np.ascontiguousarray(g.numpy().astype(np.float32)), N, n, hop, win, 1.0 / win)
+    assert rel(got_g, gx.numpy()) < 3e-6

@@ -54,6 +54,19 @@ def test_reference_run_goldens_torch_convention(se):
         assert rel(gs, k("gs")) < TOL, (i, "istft adjoint")
 
 
+def test_reference_run_goldens_without_centre_padding(se):
+    g = golden("general_geometry")
+    for i, (N, n, h, w) in enumerate(g["n_meta"]):
+        c = types.SimpleNamespace(n_fft=int(n), hop_length=int(h), win_length=int(w), center=False)
+        k = lambda name: torch.from_numpy(g[f"n{i}_{name}"]).cuda()
+        x = k("x").requires_grad_(True)
+        spec = se.stft_custom(x, c)
+        assert spec.shape == k("spec").shape
+        assert rel(spec, k("spec")) < TOL
+        (gx,) = torch.autograd.grad(spec, x, k("gspec"))
+        assert rel(gx, k("gx")) < TOL
+
+
 def test_reference_run_goldens_dccrn_convention(se):
     g = golden("general_geometry")
     for i, (N, wl, inc, nfft, wt) in enumerate(g["c_meta"]):
@@ -165,3 +178,22 @@ def test_evaluate_at_a_general_geometry(se, oref, model):
     got = se.evaluate(mix, fn.cuda() if fn else None, "cuda", config)
     assert got.shape == want.shape
     assert rel(got, want) < TOL
+
+
+@pytest.mark.parametrize("n,hop,win", [(512, 128, 512), (1024, 256, 1024), (320, 160, 320)])
+def test_stft_custom_without_centre_padding(se, oref, n, hop, win):
+    """config.center = False: the reference's stft_custom passes it to torch.stft (src/evaluate.py:116)."""
+    c = types.SimpleNamespace(n_fft=n, hop_length=hop, win_length=win, center=False)
+    x = torch.randn(3, 1, 9000, generator=torch.Generator().manual_seed(n))
+    x64 = x.double().requires_grad_(True)
+    want = oref.stft_custom_ref(x64, c)
+    xg = x.cuda().requires_grad_(True)
+    got = se.stft_custom(xg, c)
+    assert got.shape == want.shape
+    assert rel(got, want) < TOL
+    g = torch.randn(want.shape, generator=torch.Generator().manual_seed(1))
+    (g64,) = torch.autograd.grad(want, x64, g.double())
+    (gx,) = torch.autograd.grad(got, xg, g.cuda())
+    assert rel(gx, g64) < TOL
+    with pytest.raises(RuntimeError, match="overlap add"):
+        se.istft_custom(got, 9000, c)
