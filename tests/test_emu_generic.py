@@ -197,3 +197,33 @@ def test_stft_without_centre_padding(n, hop, win, N):
     (gx,) = torch.autograd.grad(want, x, g)
     got_g = E.stft_nocenter_bwd(np.ascontiguousarray(g.numpy().astype(np.float32)), N, n, hop, win, 1.0 / win)
     assert rel(got_g, gx.numpy()) < 3e-6
+
+
+def test_general_geometry_random_sweep():
+    """Seeded random geometries (even n_fft 8..260, any hop <= n_fft / 2, any win_length, ragged lengths): analysis and both
+    adjoints against the float64 restatement; synthesis where torch.istft would accept the envelope."""
+    rng = np.random.default_rng(20261017)
+    done = 0
+    while done < 14:
+        n = 2 * int(rng.integers(4, 131))
+        hop = int(rng.integers(1, n // 2 + 1))
+        win = int(rng.integers(max(2, n // 2), n + 1))
+        N = int(rng.integers(n // 2 + 1, 6 * n))
+        if (n in (512, 1024, 2048)) and (hop * 4 == n or hop * 2 == n):
+            continue
+        done += 1
+        T, F = 1 + N // hop, n // 2 + 1
+        x = rng.standard_normal((2, N)).astype(np.float32)
+        tag = (n, hop, win, N)
+        assert rel(c2(E.stft_fwd(x, n, hop, win, 1.0 / win)), o64.stft(x, n, hop, win)) < 3e-6, tag
+        spec = rng.standard_normal((2, F, T)) + 1j * rng.standard_normal((2, F, T))
+        assert rel(E.stft_bwd(r2(spec), N, n, hop, win, 1.0 / win), o64.stft_adjoint(spec, N, n, hop, win)) < 5e-6, tag
+        try:
+            want = o64.istft(spec.astype(np.complex64), n, hop, win, N)
+        except RuntimeError:
+            with pytest.raises(RuntimeError, match="overlap add"):
+                E.istft_fwd(r2(spec), N, n, hop, win, float(win))
+            continue
+        assert rel(E.istft_fwd(r2(spec), N, n, hop, win, float(win)), want) < 2e-5, tag
+        gy = rng.standard_normal((2, N)).astype(np.float32)
+        assert rel(c2(E.istft_bwd(gy, T, n, hop, win, float(win))), o64.istft_adjoint(gy, T, n, hop, win)) < 2e-5, tag
