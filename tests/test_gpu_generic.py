@@ -197,3 +197,15 @@ def test_stft_custom_without_centre_padding(se, oref, n, hop, win):
     assert rel(gx, g64) < TOL
     with pytest.raises(RuntimeError, match="overlap add"):
         se.istft_custom(got, 9000, c)
+
+
+def test_feature_epilogue_and_tuned_only_ops_at_a_general_geometry(se, oref):
+    c = cfg(256, 64, 256)
+    x = torch.randn(2, 1, 3000, generator=torch.Generator().manual_seed(4))
+    spec, feat = se.stft_custom_with_feature(x.cuda(), c, "magnitude")
+    want = oref.stft_custom_ref(x, c)
+    assert rel(spec, want) < TOL
+    assert rel(feat, oref.magnitude_feature_ref(want, "magnitude")) < TOL
+    # fused kernels that only exist for the tuned geometries say so instead of running something else
+    with pytest.raises(NotImplementedError, match="512/1024/2048"):
+        se.loss_spectral(spec, x.cuda(), c, "mse")
