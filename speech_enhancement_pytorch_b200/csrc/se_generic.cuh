@@ -70,8 +70,10 @@ __device__ __forceinline__ float2* warp_fft(float2* x, float2* y, const float2* 
             for (int i = lane; i < cnt; i += 32) {
                 const int p = i >> ls, q = i & (s - 1);
                 const float2 a = x[i], b = x[i + cnt], c = x[i + 2 * cnt], d = x[i + 3 * cnt];
-                float2 w1 = __ldg(tw + (p << ls)), w2 = __ldg(tw + 2 * (p << ls)), w3 = __ldg(tw + 3 * (p << ls));
-                if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+                // one table load; w^2 and w^3 by two complex products (cheaper than two more dependent L1 loads)
+                float2 w1 = __ldg(tw + (p << ls));
+                if (INV) w1.y = -w1.y;
+                const float2 w2 = g_mul(w1, w1), w3 = g_mul(w2, w1);
                 const float2 apc = g_add(a, c), amc = g_sub(a, c), bpd = g_add(b, d), bmd = g_sub(b, d);
                 // forward: -i (b - d); inverse: +i (b - d)
                 const float2 jb = INV ? make_float2(-bmd.y, bmd.x) : make_float2(bmd.y, -bmd.x);
@@ -230,6 +232,7 @@ __global__ void k_gen_analysis(GenArgs a) {
         if (interior) {
             const float* f = src + (base - a.pad);
             const float2* w2p = reinterpret_cast<const float2*>(a.tb.win);
+#pragma unroll 4
             for (int m = lane; m < M; m += 32) {
                 const float2 w = __ldg(w2p + m);
                 x[m] = make_float2(__ldg(f + 2 * m) * w.x, __ldg(f + 2 * m + 1) * w.y);
@@ -285,22 +288,36 @@ __global__ void k_gen_frames(GenArgs a) {
     const int row = blockIdx.x / cpr, t0 = (blockIdx.x - row * cpr) * W;
     float2* bufs = reinterpret_cast<float2*>(se_smem);
     const int F = M + 1, T = a.nframe;
-    // bins of W frames, frame index fastest in memory; lands in each warp's second buffer
+    // bins of W frames, frame index fastest in memory; lands in each warp's second buffer.  Four loads in flight per
+    // thread: the phase is latency-bound otherwise (one dependent global load per iteration)
     const int lw = (W > 4) ? 3 : (W > 2 ? 2 : W - 1);             // log2 W: W is 1, 2, 4 or 8 (gen_warps)
-    for (int e = threadIdx.x; e < F * W; e += blockDim.x) {
-        const int w = e & (W - 1), k = e >> lw, tt = t0 + w;
-        float2 v = make_float2(0.f, 0.f);
-        if (tt < T) {
-            if (a.planar) {
-                const float* s = a.in + (size_t)row * 2 * F * T;
-                v = make_float2(__ldg(s + (size_t)k * T + tt), __ldg(s + (size_t)(F + k) * T + tt));
-            } else {
-                v = __ldg(reinterpret_cast<const float2*>(a.in) + ((size_t)row * F + k) * T + tt);
+    const int FW = F * W;
+    for (int e0 = threadIdx.x; e0 < FW; e0 += 4 * blockDim.x) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j * blockDim.x;
+            const int w = e & (W - 1), k = e >> lw, tt = t0 + w;
+            v[j] = make_float2(0.f, 0.f);
+            if (e < FW && tt < T) {
+                if (a.planar) {
+                    const float* s = a.in + (size_t)row * 2 * F * T;
+                    v[j] = make_float2(__ldg(s + (size_t)k * T + tt), __ldg(s + (size_t)(F + k) * T + tt));
+                } else {
+                    v[j] = __ldg(reinterpret_cast<const float2*>(a.in) + ((size_t)row * F + k) * T + tt);
+                }
             }
-            if (k == 0 || k == M) v = make_float2(v.x * a.edge_w, 0.f);        // imaginary parts of DC / Nyquist are ignored
-            else v = make_float2(v.x * a.mid_w, v.y * a.mid_w);
         }
-        bufs[(size_t)w * 2 * BL + BL + k] = v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j * blockDim.x;
+            if (e >= FW) continue;
+            const int w = e & (W - 1), k = e >> lw;
+            float2 u = v[j];
+            if (k == 0 || k == M) u = make_float2(u.x * a.edge_w, 0.f);        // imaginary parts of DC / Nyquist are ignored
+            else u = make_float2(u.x * a.mid_w, u.y * a.mid_w);
+            bufs[(size_t)w * 2 * BL + BL + k] = u;
+        }
     }
     __syncthreads();
     const int t = t0 + warp;
@@ -341,6 +358,7 @@ __device__ __forceinline__ void gen_ola_env_at(const GenArgs& a, const float* __
     t_hi = t_hi < T - 1 ? t_hi : T - 1;
     int t_lo = i - a.f_lo - a.f_len + 1;
     t_lo = t_lo <= 0 ? 0 : (t_lo + hop - 1) / hop;
+#pragma unroll 4
     for (int t = t_hi; t >= t_lo; --t) {
         const int j = i - t * hop;
         acc += __ldg(frames + (size_t)t * a.f_len + (j - a.f_lo));

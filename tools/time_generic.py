@@ -22,3 +22,9 @@ x16=torch.randn(16,1,64000).cuda()
 with torch.no_grad():
     sp=st(x16)
     print("conv 320/160/512 16 rows: stft %.1f us istft %.1f us" % (timed(lambda: st(x16)), timed(lambda: ist(sp))))
+for n, h, w in ((320, 160, 320), (400, 100, 400)):
+    c = cfg(n, h, w)
+    with torch.no_grad():
+        spec = se.stft_custom(x, c)
+        t1 = timed(lambda: se.stft_custom(x, c)); t2 = timed(lambda: se.istft_custom(spec, 64000, c))
+    print(f"n={n} hop={h} win={w} (Bluestein): stft {t1:.1f} us, istft {t2:.1f} us", flush=True)
